@@ -1,0 +1,188 @@
+/*
+ * ntt_b200.h -- C-ABI of the B200-native negacyclic NTT (Z_q[X]/(X^N+1)).
+ *
+ * This is the drop-in boundary for the hot path of IBM/optimized-number-theoretic-transform-implementations:
+ * plain pointers and sizes, `int` status codes, no C++/CUDA/torch types.  Every entry point names the
+ * reference interface it replaces (paths relative to the reference root).
+ *
+ * Conventions kept from the reference:
+ *   - coefficients are uint64_t, transforms are IN PLACE, the caller owns every buffer
+ *     (include/ntt_reference.h:13-39);
+ *   - w[] is the bit-reversed table of powers of psi, w[bitrev(i)] = psi^i, and w_con[] its Shoup
+ *     companion floor(w*2^64/q) (include/internal/pre_compute.h:38-77);
+ *   - forward: natural-order input in [0,4q) -> bit-reversed-order output; inverse: bit-reversed input
+ *     in [0,2q) -> natural output in [0,q), scaled by N^-1 (src/ntt_reference.c:11-66);
+ *   - status codes NTT_B200_SUCCESS 0 / NTT_B200_ERROR -1 (include/internal/defs.h:20-21).
+ *
+ * There is no CPU fallback: every call below runs hand-written sm_100a kernels and fails with
+ * NTT_B200_ERROR (see ntt_b200_last_error) when no CUDA device is usable.
+ */
+#ifndef NTT_B200_H
+#define NTT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NTT_B200_SUCCESS 0
+#define NTT_B200_ERROR   (-1)
+
+#define NTT_B200_MIN_LOGN 1
+#define NTT_B200_MAX_LOGN 24
+
+typedef struct ntt_b200_plan ntt_b200_plan_t; /* opaque; one per (device, N, q, psi) */
+
+/* ---- library ------------------------------------------------------------------------------------ */
+
+/* Human-readable reason of the last NTT_B200_ERROR on the calling thread ("" if none). */
+const char *ntt_b200_last_error(void);
+/* Number of usable CUDA devices (0 if none / driver missing). */
+int ntt_b200_device_count(void);
+/* "ntt_b200 <version> sm_100a" */
+const char *ntt_b200_version(void);
+
+/* ---- plans ---------------------------------------------------------------------------------------- */
+
+/*
+ * Build a plan from reference-format tables (host pointers; copied, never retained).
+ * Replaces the per-call table arguments of fwd_ntt_ref_harvey / inv_ntt_ref_harvey
+ * (include/ntt_reference.h:13-39) and the fixture set-up of tests/test_cases.h:212-238:
+ *   w, w_con         forward tables (N words each) -- calc_w + calc_w_con(…, 64)
+ *   w_inv, w_inv_con inverse tables (powers of psi^-1); may both be NULL for a forward-only plan
+ *   n_inv, n_inv_con N^-1 mod q and its Shoup companion (mul_op_t .op/.con,
+ *                    include/internal/fast_mul_operators.h:10-13); ignored when w_inv is NULL
+ * Preconditions as in the reference: N = 2^m (1 <= m <= 24), q odd, q < 2^62, tables consistent with q.
+ * The *_con tables are validated against w (they must equal floor(w*2^64/q)) and otherwise unused:
+ * the device keeps its own twiddle layout.
+ */
+int ntt_b200_plan_create(ntt_b200_plan_t **plan, int device, uint64_t N, uint64_t q, const uint64_t *w,
+                         const uint64_t *w_con, const uint64_t *w_inv, const uint64_t *w_inv_con, uint64_t n_inv,
+                         uint64_t n_inv_con);
+
+/*
+ * Build a plan from the primitive 2N-th root psi alone; all tables (both directions) and N^-1 are
+ * generated ON THE DEVICE.  Replaces calc_w / calc_w_inv / calc_w_con / calc_ninv_con
+ * (include/internal/pre_compute.h:38-83).  Fails if psi^N != -1 (mod q).
+ */
+int ntt_b200_plan_create_psi(ntt_b200_plan_t **plan, int device, uint64_t N, uint64_t q, uint64_t psi);
+
+int ntt_b200_plan_destroy(ntt_b200_plan_t *plan);
+
+/* Plan attributes. */
+uint64_t ntt_b200_plan_n(const ntt_b200_plan_t *plan);
+uint64_t ntt_b200_plan_q(const ntt_b200_plan_t *plan);
+int      ntt_b200_plan_device(const ntt_b200_plan_t *plan);
+/* 1 if the plan uses the lazy fast path (q small enough that no per-stage correction is needed),
+ * 0 if it uses the general Harvey path (any q < 2^62). */
+int ntt_b200_plan_is_lazy(const ntt_b200_plan_t *plan);
+
+/*
+ * Copy the plan's tables back to the host in REFERENCE format (each pointer may be NULL to skip):
+ * what calc_w / calc_w_con / calc_w_inv would have produced (include/internal/pre_compute.h:38-77).
+ * For plans built by ntt_b200_plan_create_psi this returns the device-generated tables.
+ */
+int ntt_b200_plan_export_tables(const ntt_b200_plan_t *plan, uint64_t *w, uint64_t *w_con, uint64_t *w_inv,
+                                uint64_t *w_inv_con, uint64_t *n_inv, uint64_t *n_inv_con);
+
+/* ---- batched transforms, DEVICE-resident data (the measured path) ------------------------------------- */
+
+/*
+ * d_a: device pointer on the plan's device, `batch` polynomials of N words each, contiguous,
+ * 16-byte aligned.  stream: a cudaStream_t passed as void* (NULL = default stream).  Asynchronous.
+ *
+ * fwd_batch      = fwd_ntt_ref_harvey      on each polynomial (include/ntt_reference.h:19-31): out in [0,q)
+ * fwd_lazy_batch = fwd_ntt_ref_harvey_lazy (src/ntt_reference.c:11-31): contract is "out in [0,4q)";
+ *                  this implementation returns the fully reduced representative, which satisfies it
+ * inv_batch      = inv_ntt_ref_harvey      (src/ntt_reference.c:33-66): out in [0,q)
+ */
+int ntt_b200_fwd_batch(const ntt_b200_plan_t *plan, uint64_t *d_a, size_t batch, void *stream);
+int ntt_b200_fwd_lazy_batch(const ntt_b200_plan_t *plan, uint64_t *d_a, size_t batch, void *stream);
+int ntt_b200_inv_batch(const ntt_b200_plan_t *plan, uint64_t *d_a, size_t batch, void *stream);
+
+/*
+ * RNS form: limb l of every polynomial uses plans[l] (its own q).  d_a holds `limbs` consecutive
+ * blocks of `batch_per_limb` polynomials.  All plans must share N and device.
+ */
+int ntt_b200_fwd_rns(ntt_b200_plan_t *const *plans, size_t limbs, uint64_t *d_a, size_t batch_per_limb,
+                     void *stream);
+int ntt_b200_inv_rns(ntt_b200_plan_t *const *plans, size_t limbs, uint64_t *d_a, size_t batch_per_limb,
+                     void *stream);
+
+/*
+ * Negacyclic product c = a * b in Z_q[X]/(X^N+1) for `batch` pairs (next row of the scope table:
+ * fwd x2, pointwise multiply, inverse).  d_c may alias d_a.  d_a and d_b are overwritten
+ * (they hold the forward transforms afterwards when d_c != d_a).
+ */
+int ntt_b200_negacyclic_mul_batch(const ntt_b200_plan_t *plan, uint64_t *d_c, uint64_t *d_a, uint64_t *d_b,
+                                  size_t batch, void *stream);
+/* c[i] = a[i]*b[i] mod q over batch*N words (NTT-domain product); inputs in [0,q). */
+int ntt_b200_pointwise_mul_batch(const ntt_b200_plan_t *plan, uint64_t *d_c, const uint64_t *d_a,
+                                 const uint64_t *d_b, size_t batch, void *stream);
+
+/* ---- batched transforms, HOST-resident data (end-to-end path) ---------------------------------------- */
+
+/*
+ * Same transforms on host memory: H2D copy, kernels, D2H copy, synchronous.  h_a may be pageable or
+ * pinned (pinned is faster); large batches are pipelined in chunks over two streams.
+ */
+int ntt_b200_fwd_batch_host(const ntt_b200_plan_t *plan, uint64_t *h_a, size_t batch);
+int ntt_b200_inv_batch_host(const ntt_b200_plan_t *plan, uint64_t *h_a, size_t batch);
+
+/* Pinned host memory helpers (cudaHostAlloc / cudaFreeHost) so C callers need no CUDA headers. */
+int ntt_b200_host_alloc(void **ptr, size_t bytes);
+int ntt_b200_host_free(void *ptr);
+/* Device memory helpers for C callers of the device-resident API. */
+int ntt_b200_device_alloc(int device, void **d_ptr, size_t bytes);
+int ntt_b200_device_free(int device, void *d_ptr);
+int ntt_b200_memcpy_h2d(int device, void *d_dst, const void *h_src, size_t bytes);
+int ntt_b200_memcpy_d2h(int device, void *h_dst, const void *d_src, size_t bytes);
+int ntt_b200_device_sync(int device);
+
+/* ---- reference-shaped single-polynomial entry points (host pointers) --------------------------------- */
+
+/*
+ * Same argument lists as the reference functions they replace; each call looks up (or builds and
+ * caches) a plan keyed on (N, q, w[N/2]), copies the polynomial to the device, transforms, copies back.
+ *
+ *   ntt_b200_fwd_ntt_ref_harvey_lazy  <- fwd_ntt_ref_harvey_lazy  src/ntt_reference.c:11
+ *   ntt_b200_fwd_ntt_ref_harvey       <- fwd_ntt_ref_harvey       include/ntt_reference.h:19
+ *   ntt_b200_inv_ntt_ref_harvey       <- inv_ntt_ref_harvey       src/ntt_reference.c:33
+ *                                        (n_inv/n_inv_con = mul_op_t .op/.con; word_size must be 64)
+ *   ntt_b200_fwd_ntt_ref_harvey_dbl   <- fwd_ntt_ref_harvey_dbl   include/ntt_reference.h:51
+ *
+ * The library libntt_b200_dropin.so additionally exports these under the reference's own symbol names
+ * and with its mul_op_t-by-value signature, so the reference's test and bench
+ * drivers link against it unchanged.  Return: NTT_B200_SUCCESS / NTT_B200_ERROR.
+ */
+int ntt_b200_fwd_ntt_ref_harvey_lazy(uint64_t a[], uint64_t N, uint64_t q, const uint64_t w[],
+                                     const uint64_t w_con[]);
+int ntt_b200_fwd_ntt_ref_harvey(uint64_t a[], uint64_t N, uint64_t q, const uint64_t w[], const uint64_t w_con[]);
+int ntt_b200_inv_ntt_ref_harvey(uint64_t a[], uint64_t N, uint64_t q, uint64_t n_inv, uint64_t n_inv_con,
+                                uint64_t word_size, const uint64_t w[], const uint64_t w_con[]);
+int ntt_b200_fwd_ntt_ref_harvey_dbl(uint64_t a1[], uint64_t a2[], uint64_t N, uint64_t q, const uint64_t w[],
+                                    const uint64_t w_con[]);
+/* Drop every cached plan created by the reference-shaped entry points. */
+void ntt_b200_dropin_reset(void);
+
+/* ---- host-side table builders (C replacements of include/internal/pre_compute.h:16-83) ---------------- */
+
+uint64_t ntt_b200_bit_rev_idx(uint64_t idx, uint64_t width);
+/* out[bitrev_m(i)] = root^i mod q, i < N (calc_w / calc_w_inv) */
+int ntt_b200_calc_w(uint64_t *out, uint64_t root, uint64_t N, uint64_t q);
+/* out[i] = floor(w[i] * 2^word_size / q) (calc_w_con) */
+int      ntt_b200_calc_w_con(uint64_t *out, const uint64_t *w, uint64_t N, uint64_t q, uint64_t word_size);
+uint64_t ntt_b200_calc_ninv_con(uint64_t n_inv, uint64_t q, uint64_t word_size);
+/* number theory helpers for callers that only know (N, q) */
+uint64_t ntt_b200_pow_mod(uint64_t a, uint64_t e, uint64_t q);
+uint64_t ntt_b200_inv_mod(uint64_t a, uint64_t q); /* q prime */
+int      ntt_b200_is_prime(uint64_t n);
+/* smallest primitive 2N-th root of unity mod q (the rule of tests/test_cases.h:113-142); 0 if none */
+uint64_t ntt_b200_min_primitive_root(uint64_t N, uint64_t q);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NTT_B200_H */

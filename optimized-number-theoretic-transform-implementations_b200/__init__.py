@@ -1,0 +1,281 @@
+"""B200-native negacyclic NTT -- Python view of the C-ABI in include/ntt_b200.h.
+
+The product is the shared library ``libntt_b200.so`` (C host code + hand-written sm_100a kernels) built
+in this directory by ``make``.  This module only binds it with ctypes so tests, ``bench.py`` and
+``torch.distributed`` plumbing can drive it; PyTorch is used for device memory and streams, never for
+arithmetic.  There is no fallback: if the library is missing the import raises, and every call raises
+``NttError`` when the library reports NTT_B200_ERROR (e.g. no CUDA device).
+
+Entry points mirror the reference's operator interface (include/ntt_reference.h:13-65):
+``fwd_ntt_ref_harvey``, ``fwd_ntt_ref_harvey_lazy``, ``inv_ntt_ref_harvey``, ``fwd_ntt_ref_harvey_dbl``
+on host arrays, plus the plan/batch API for device-resident data.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libntt_b200.so")
+DROPIN_PATH = os.path.join(_HERE, "libntt_b200_dropin.so")
+
+u64 = C.c_uint64
+_U64P = np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")
+
+
+class NttError(RuntimeError):
+    pass
+
+
+def build(verbose=False):
+    """Compile libntt_b200.so / libntt_b200_dropin.so in-tree (nvcc -gencode arch=compute_100a,code=sm_100a)."""
+    subprocess.run(["make", "-C", _HERE, "all"], check=True, stdout=None if verbose else subprocess.DEVNULL)
+
+
+def _bind():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("%s not built: run `make -C %s` (needs nvcc); there is no CPU fallback" % (LIB_PATH, _HERE))
+    L = C.CDLL(LIB_PATH)
+    vp, sz, i = C.c_void_p, C.c_size_t, C.c_int
+    L.ntt_b200_last_error.restype = C.c_char_p
+    L.ntt_b200_version.restype = C.c_char_p
+    L.ntt_b200_device_count.restype = i
+    L.ntt_b200_plan_create.argtypes = [C.POINTER(vp), i, u64, u64, vp, vp, vp, vp, u64, u64]
+    L.ntt_b200_plan_create_psi.argtypes = [C.POINTER(vp), i, u64, u64, u64]
+    L.ntt_b200_plan_destroy.argtypes = [vp]
+    for f in ("ntt_b200_plan_n", "ntt_b200_plan_q"):
+        getattr(L, f).restype = u64
+        getattr(L, f).argtypes = [vp]
+    L.ntt_b200_plan_device.argtypes = [vp]
+    L.ntt_b200_plan_is_lazy.argtypes = [vp]
+    L.ntt_b200_plan_export_tables.argtypes = [vp, vp, vp, vp, vp, C.POINTER(u64), C.POINTER(u64)]
+    for f in ("ntt_b200_fwd_batch", "ntt_b200_fwd_lazy_batch", "ntt_b200_inv_batch"):
+        getattr(L, f).argtypes = [vp, vp, sz, vp]
+    for f in ("ntt_b200_fwd_rns", "ntt_b200_inv_rns"):
+        getattr(L, f).argtypes = [C.POINTER(vp), sz, vp, sz, vp]
+    L.ntt_b200_negacyclic_mul_batch.argtypes = [vp, vp, vp, vp, sz, vp]
+    L.ntt_b200_pointwise_mul_batch.argtypes = [vp, vp, vp, vp, sz, vp]
+    for f in ("ntt_b200_fwd_batch_host", "ntt_b200_inv_batch_host"):
+        getattr(L, f).argtypes = [vp, vp, sz]
+    L.ntt_b200_host_alloc.argtypes = [C.POINTER(vp), sz]
+    L.ntt_b200_host_free.argtypes = [vp]
+    L.ntt_b200_device_alloc.argtypes = [i, C.POINTER(vp), sz]
+    L.ntt_b200_device_free.argtypes = [i, vp]
+    L.ntt_b200_memcpy_h2d.argtypes = [i, vp, vp, sz]
+    L.ntt_b200_memcpy_d2h.argtypes = [i, vp, vp, sz]
+    L.ntt_b200_device_sync.argtypes = [i]
+    L.ntt_b200_fwd_ntt_ref_harvey_lazy.argtypes = [_U64P, u64, u64, _U64P, _U64P]
+    L.ntt_b200_fwd_ntt_ref_harvey.argtypes = [_U64P, u64, u64, _U64P, _U64P]
+    L.ntt_b200_inv_ntt_ref_harvey.argtypes = [_U64P, u64, u64, u64, u64, u64, _U64P, _U64P]
+    L.ntt_b200_fwd_ntt_ref_harvey_dbl.argtypes = [_U64P, _U64P, u64, u64, _U64P, _U64P]
+    L.ntt_b200_dropin_reset.restype = None
+    L.ntt_b200_bit_rev_idx.restype = u64
+    L.ntt_b200_bit_rev_idx.argtypes = [u64, u64]
+    L.ntt_b200_calc_w.argtypes = [_U64P, u64, u64, u64]
+    L.ntt_b200_calc_w_con.argtypes = [_U64P, _U64P, u64, u64, u64]
+    for f in ("ntt_b200_calc_ninv_con", "ntt_b200_pow_mod"):
+        getattr(L, f).restype = u64
+        getattr(L, f).argtypes = [u64, u64, u64]
+    for f in ("ntt_b200_inv_mod", "ntt_b200_min_primitive_root"):
+        getattr(L, f).restype = u64
+        getattr(L, f).argtypes = [u64, u64]
+    L.ntt_b200_is_prime.argtypes = [u64]
+    return L
+
+
+lib = _bind()
+
+#: every symbol include/ntt_b200.h declares (checked against the header and the .so by the CPU tests)
+EXPORTS = [
+    "ntt_b200_last_error", "ntt_b200_device_count", "ntt_b200_version",
+    "ntt_b200_plan_create", "ntt_b200_plan_create_psi", "ntt_b200_plan_destroy",
+    "ntt_b200_plan_n", "ntt_b200_plan_q", "ntt_b200_plan_device", "ntt_b200_plan_is_lazy",
+    "ntt_b200_plan_export_tables",
+    "ntt_b200_fwd_batch", "ntt_b200_fwd_lazy_batch", "ntt_b200_inv_batch",
+    "ntt_b200_fwd_rns", "ntt_b200_inv_rns",
+    "ntt_b200_negacyclic_mul_batch", "ntt_b200_pointwise_mul_batch",
+    "ntt_b200_fwd_batch_host", "ntt_b200_inv_batch_host",
+    "ntt_b200_host_alloc", "ntt_b200_host_free", "ntt_b200_device_alloc", "ntt_b200_device_free",
+    "ntt_b200_memcpy_h2d", "ntt_b200_memcpy_d2h", "ntt_b200_device_sync",
+    "ntt_b200_fwd_ntt_ref_harvey_lazy", "ntt_b200_fwd_ntt_ref_harvey", "ntt_b200_inv_ntt_ref_harvey",
+    "ntt_b200_fwd_ntt_ref_harvey_dbl", "ntt_b200_dropin_reset",
+    "ntt_b200_bit_rev_idx", "ntt_b200_calc_w", "ntt_b200_calc_w_con", "ntt_b200_calc_ninv_con",
+    "ntt_b200_pow_mod", "ntt_b200_inv_mod", "ntt_b200_is_prime", "ntt_b200_min_primitive_root",
+]
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise NttError("%s: %s" % (what, lib.ntt_b200_last_error().decode()))
+
+
+def device_count():
+    return int(lib.ntt_b200_device_count())
+
+
+def version():
+    return lib.ntt_b200_version().decode()
+
+
+def _ptr(x):
+    """Raw address of a torch tensor (device or host), a numpy array, an int, or None."""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if isinstance(x, np.ndarray):
+        assert x.dtype == np.uint64 and x.flags["C_CONTIGUOUS"]
+        return x.ctypes.data
+    return x.data_ptr()  # torch tensor (int64 storage viewed as uint64 words)
+
+
+def _stream_ptr(stream):
+    if stream is None:
+        return None
+    return getattr(stream, "cuda_stream", stream)
+
+
+# ---- host-side table builders (C replacements of include/internal/pre_compute.h) -------------------
+
+def calc_w(root, N, q):
+    out = np.empty(N, dtype=np.uint64)
+    _check(lib.ntt_b200_calc_w(out, root, N, q), "calc_w")
+    return out
+
+
+def calc_w_con(w, q, word_size=64):
+    w = np.ascontiguousarray(w, dtype=np.uint64)
+    out = np.empty_like(w)
+    _check(lib.ntt_b200_calc_w_con(out, w, w.shape[0], q, word_size), "calc_w_con")
+    return out
+
+
+def calc_ninv_con(n_inv, q, word_size=64):
+    return int(lib.ntt_b200_calc_ninv_con(n_inv, q, word_size))
+
+
+def pow_mod(a, e, q):
+    return int(lib.ntt_b200_pow_mod(a, e, q))
+
+
+def inv_mod(a, q):
+    return int(lib.ntt_b200_inv_mod(a, q))
+
+
+def is_prime(n):
+    return bool(lib.ntt_b200_is_prime(n))
+
+
+def min_primitive_root(N, q):
+    return int(lib.ntt_b200_min_primitive_root(N, q))
+
+
+# ---- plans -------------------------------------------------------------------------------------------
+
+class Plan:
+    """One (device, N, q, psi): owns the device twiddle tables.  See ntt_b200_plan_create[_psi]."""
+
+    def __init__(self, handle, N, q):
+        self._h = handle
+        self.N, self.q = N, q
+
+    @classmethod
+    def from_tables(cls, N, q, w=None, w_con=None, w_inv=None, w_inv_con=None, n_inv=0, n_inv_con=0, device=0):
+        keep = [None if t is None else np.ascontiguousarray(t, dtype=np.uint64) for t in (w, w_con, w_inv, w_inv_con)]
+        h = C.c_void_p()
+        _check(lib.ntt_b200_plan_create(C.byref(h), device, N, q, *[_ptr(t) for t in keep], n_inv, n_inv_con),
+               "plan_create")
+        return cls(h, N, q)
+
+    @classmethod
+    def from_psi(cls, N, q, psi, device=0):
+        h = C.c_void_p()
+        _check(lib.ntt_b200_plan_create_psi(C.byref(h), device, N, q, psi), "plan_create_psi")
+        return cls(h, N, q)
+
+    def close(self):
+        if self._h:
+            lib.ntt_b200_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def is_lazy(self):
+        return bool(lib.ntt_b200_plan_is_lazy(self._h))
+
+    @property
+    def device(self):
+        return int(lib.ntt_b200_plan_device(self._h))
+
+    def export_tables(self, inverse=True):
+        w = np.empty(self.N, dtype=np.uint64)
+        wc = np.empty(self.N, dtype=np.uint64)
+        wi = np.empty(self.N, dtype=np.uint64) if inverse else None
+        wic = np.empty(self.N, dtype=np.uint64) if inverse else None
+        n_inv, n_inv_con = u64(), u64()
+        _check(lib.ntt_b200_plan_export_tables(self._h, _ptr(w), _ptr(wc), _ptr(wi), _ptr(wic), C.byref(n_inv),
+                                               C.byref(n_inv_con)), "export_tables")
+        return dict(w=w, w_con=wc, w_inv=wi, w_inv_con=wic, n_inv=int(n_inv.value), n_inv_con=int(n_inv_con.value))
+
+    # device-resident data: `d_a` is a torch cuda tensor (int64 storage) or a raw device address
+    def fwd(self, d_a, batch, stream=None):
+        _check(lib.ntt_b200_fwd_batch(self._h, _ptr(d_a), batch, _stream_ptr(stream)), "fwd_batch")
+
+    def fwd_lazy(self, d_a, batch, stream=None):
+        _check(lib.ntt_b200_fwd_lazy_batch(self._h, _ptr(d_a), batch, _stream_ptr(stream)), "fwd_lazy_batch")
+
+    def inv(self, d_a, batch, stream=None):
+        _check(lib.ntt_b200_inv_batch(self._h, _ptr(d_a), batch, _stream_ptr(stream)), "inv_batch")
+
+    def negacyclic_mul(self, d_c, d_a, d_b, batch, stream=None):
+        _check(lib.ntt_b200_negacyclic_mul_batch(self._h, _ptr(d_c), _ptr(d_a), _ptr(d_b), batch,
+                                                 _stream_ptr(stream)), "negacyclic_mul_batch")
+
+    def pointwise_mul(self, d_c, d_a, d_b, batch, stream=None):
+        _check(lib.ntt_b200_pointwise_mul_batch(self._h, _ptr(d_c), _ptr(d_a), _ptr(d_b), batch,
+                                                _stream_ptr(stream)), "pointwise_mul_batch")
+
+    # host-resident data: numpy uint64 array or pinned torch tensor, transformed in place
+    def fwd_host(self, h_a, batch):
+        _check(lib.ntt_b200_fwd_batch_host(self._h, _ptr(h_a), batch), "fwd_batch_host")
+
+    def inv_host(self, h_a, batch):
+        _check(lib.ntt_b200_inv_batch_host(self._h, _ptr(h_a), batch), "inv_batch_host")
+
+
+def fwd_rns(plans, d_a, batch_per_limb, stream=None):
+    arr = (C.c_void_p * len(plans))(*[p._h for p in plans])
+    _check(lib.ntt_b200_fwd_rns(arr, len(plans), _ptr(d_a), batch_per_limb, _stream_ptr(stream)), "fwd_rns")
+
+
+def inv_rns(plans, d_a, batch_per_limb, stream=None):
+    arr = (C.c_void_p * len(plans))(*[p._h for p in plans])
+    _check(lib.ntt_b200_inv_rns(arr, len(plans), _ptr(d_a), batch_per_limb, _stream_ptr(stream)), "inv_rns")
+
+
+# ---- reference-shaped entry points (host numpy arrays, in place) -----------------------------------
+
+def fwd_ntt_ref_harvey(a, N, q, w, w_con):
+    _check(lib.ntt_b200_fwd_ntt_ref_harvey(a, N, q, w, w_con), "fwd_ntt_ref_harvey")
+
+
+def fwd_ntt_ref_harvey_lazy(a, N, q, w, w_con):
+    _check(lib.ntt_b200_fwd_ntt_ref_harvey_lazy(a, N, q, w, w_con), "fwd_ntt_ref_harvey_lazy")
+
+
+def fwd_ntt_ref_harvey_dbl(a1, a2, N, q, w, w_con):
+    _check(lib.ntt_b200_fwd_ntt_ref_harvey_dbl(a1, a2, N, q, w, w_con), "fwd_ntt_ref_harvey_dbl")
+
+
+def inv_ntt_ref_harvey(a, N, q, n_inv, n_inv_con, word_size, w, w_con):
+    _check(lib.ntt_b200_inv_ntt_ref_harvey(a, N, q, n_inv, n_inv_con, word_size, w, w_con), "inv_ntt_ref_harvey")
+
+
+def dropin_reset():
+    lib.ntt_b200_dropin_reset()

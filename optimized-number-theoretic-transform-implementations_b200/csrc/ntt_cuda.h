@@ -1,0 +1,84 @@
+/*
+ * csrc/ntt_cuda.h -- the thin CUDA layer under the C host code.
+ *
+ * Everything here is extern "C" with POD arguments only, so the host side (the .c files under host/, compiled by gcc as
+ * C) never sees CUDA C++ headers.  Device pointers travel as void* / uint64_t*, streams as void*.
+ * All functions return 0 on success, -1 on failure with the reason retrievable via ntt_cuda_error().
+ */
+#ifndef NTT_CUDA_H
+#define NTT_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NTT_MAX_STAGES 24
+
+/* One modular multiplier in the device's "split" form (lazy path), see csrc/ntt_device.cuh:
+ *   w  : the multiplier, u = w * 2^32 mod q, wq = floor(w * 2^31 / q), uq = floor(u * 2^31 / q)
+ * or, on the exact (Harvey) path: w and c = floor(w * 2^64 / q) in (u0,u1). */
+typedef struct ntt_cuda_mulc {
+  uint32_t w0, w1, u0, u1;
+  uint32_t wq, uq;
+} ntt_cuda_mulc_t;
+
+/* Everything a kernel needs to know about one (N, q); passed by value as a kernel parameter. */
+typedef struct ntt_cuda_params {
+  uint64_t q;
+  uint64_t neg2q;   /* 2^64 - 2q (lazy path) */
+  uint64_t negq;    /* 2^64 - q */
+  uint32_t logn;
+  uint32_t lazy;    /* 1: lazy split-multiplier path, 0: exact Harvey path */
+  uint32_t red_shift; /* final reduction: vt = v >> red_shift, Q = hi32(vt * red_mu) */
+  uint32_t red_mu;
+  /* forward twiddles: wu[N] (uint4: w0,w1,u0,u1) and qq[N] (uint2: wq,uq), reference index order */
+  const void *fwd_wu;
+  const void *fwd_qq;
+  const void *inv_wu;
+  const void *inv_qq;
+  /* inverse last stage: N^-1 and N^-1 * w_inv[1] as multipliers */
+  ntt_cuda_mulc_t ninv;
+  ntt_cuda_mulc_t ninv_w1;
+  /* inverse lazy bookkeeping, indexed by global stage s (processed m-1 .. 0):
+   * inv_c[s] = B_s * q with B_s the value bound (in units of q) before stage s */
+  uint64_t inv_c[NTT_MAX_STAGES];
+  uint32_t inv_renorm_mask; /* bit s set: bring values below 3q before running stage s */
+} ntt_cuda_params_t;
+
+const char *ntt_cuda_error(void);
+int         ntt_cuda_device_count(void);
+
+int ntt_cuda_malloc(int device, void **d_ptr, size_t bytes);
+int ntt_cuda_free(int device, void *d_ptr);
+int ntt_cuda_host_alloc(void **h_ptr, size_t bytes);
+int ntt_cuda_host_free(void *h_ptr);
+int ntt_cuda_h2d(int device, void *d_dst, const void *h_src, size_t bytes, void *stream);
+int ntt_cuda_d2h(int device, void *h_dst, const void *d_src, size_t bytes, void *stream);
+int ntt_cuda_sync(int device, void *stream);
+int ntt_cuda_stream_create(int device, void **stream);
+int ntt_cuda_stream_destroy(int device, void *stream);
+
+/* Fill p->inv_c[] and p->inv_renorm_mask from p->q and p->logn (lazy path bookkeeping). */
+int ntt_cuda_plan_inverse_bounds(ntt_cuda_params_t *p);
+
+/* Build device twiddle tables (wu, qq) of N entries from a reference-format table w[] that is already
+ * on the device (d_w).  d_con_out (may be NULL) receives floor(w*2^64/q) for validation/export. */
+int ntt_cuda_build_tables(int device, const ntt_cuda_params_t *p, const uint64_t *d_w, void *d_wu, void *d_qq,
+                          uint64_t *d_con_out, uint64_t N, void *stream);
+/* Generate the reference-format table d_w[bitrev(i)] = root^i mod q on the device. */
+int ntt_cuda_gen_root_table(int device, uint64_t *d_w, uint64_t root, uint64_t N, uint64_t q, void *stream);
+
+/* Transforms over `batch` contiguous polynomials of N = 2^logn words at d_a (in place). */
+int ntt_cuda_forward(int device, const ntt_cuda_params_t *p, uint64_t *d_a, size_t batch, void *stream);
+int ntt_cuda_inverse(int device, const ntt_cuda_params_t *p, uint64_t *d_a, size_t batch, void *stream);
+/* c = a .* b mod q over n words; inputs < q (any q < 2^62). */
+int ntt_cuda_pointwise(int device, const ntt_cuda_params_t *p, uint64_t *d_c, const uint64_t *d_a,
+                       const uint64_t *d_b, size_t n, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

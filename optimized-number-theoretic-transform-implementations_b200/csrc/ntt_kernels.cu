@@ -1,0 +1,700 @@
+/*
+ * csrc/ntt_kernels.cu -- sm_100a kernels and their extern "C" launchers (see ntt_cuda.h).
+ *
+ * Kernel inventory
+ *   k_chunk<L,...>     one CTA transforms one contiguous chunk of 2^L coefficients (L <= 14, i.e. up to a
+ *                      whole N = 2^14 polynomial) held in shared memory: up to three register-tiled
+ *                      passes (radix 2^5, 2^5, 2^4) with one __syncthreads between passes.
+ *   k_strided<R,...>   register-only radix-2^R pass over global memory for the stages whose butterfly
+ *                      distance exceeds a chunk (N >= 2^15): the "two-kernel split" of the north star.
+ *                      Each thread owns 2^R coefficients at stride N/2^(s0+R); warps read and write
+ *                      consecutive addresses.
+ *   k_build_tables, k_gen_roots   on-device twiddle table generation
+ *                      (replaces calc_w / calc_w_con, include/internal/pre_compute.h:38-77).
+ *   k_pointwise        NTT-domain product.
+ *
+ * Stage/twiddle schedule (restates src/ntt_reference.c:19-30 and :43-53): forward stage s has 2^s blocks
+ * of 2t coefficients, t = N/2^(s+1); block i multiplies its upper half by w[2^s + i].  The inverse runs
+ * the stages backwards with Gentleman-Sande butterflies and the tables of psi^-1, and folds N^-1 into
+ * stage 0.
+ */
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+
+#include "ntt_cuda.h"
+#include "ntt_device.cuh"
+
+using namespace nttb200;
+
+/* ------------------------------------------------------------------------------------------------ */
+/* error plumbing                                                                                    */
+/* ------------------------------------------------------------------------------------------------ */
+
+static thread_local char g_err[512] = "";
+
+static int fail(const char *what, cudaError_t e)
+{
+  snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+  return -1;
+}
+static int fail_msg(const char *what)
+{
+  snprintf(g_err, sizeof(g_err), "%s", what);
+  return -1;
+}
+#define CU(call)                             \
+  do {                                       \
+    cudaError_t e_ = (call);                 \
+    if(e_ != cudaSuccess) return fail(#call, e_); \
+  } while(0)
+
+extern "C" const char *ntt_cuda_error(void) { return g_err; }
+
+extern "C" int ntt_cuda_device_count(void)
+{
+  int n = 0;
+  if(cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* shared-memory layout                                                                              */
+/* ------------------------------------------------------------------------------------------------ */
+
+/* Coefficient e of a chunk lives at 8-byte slot swz(e): the 16-byte unit index (e>>1) has its low three
+ * bits XORed with bits 3..5 of itself, i.e. exactly the TMA SWIZZLE_128B pattern over 128-byte rows.
+ * Effect: a thread reading 16 consecutive coefficients (one 128-byte row) with LDS.128 hits a different
+ * bank group than its seven neighbours, and strided passes still see whole rows. */
+__device__ __forceinline__ uint32_t swz(uint32_t e) { return e ^ (((e >> 4) & 7u) << 1); }
+
+/* ------------------------------------------------------------------------------------------------ */
+/* register-tiled radix-2^R butterfly network                                                        */
+/* ------------------------------------------------------------------------------------------------ */
+
+/* Twiddle fetch for global stage s, block blk */
+template <bool EXACT>
+__device__ __forceinline__ Mulc tw(const ntt_cuda_params_t &p, bool fwd, uint32_t s, uint32_t blk)
+{
+  const uint32_t idx = (1u << s) + blk;
+  const uint4 *  wu  = (const uint4 *)(fwd ? p.fwd_wu : p.inv_wu);
+  if(EXACT) return load_mulc_exact(wu, idx);
+  const uint2 *qq = (const uint2 *)(fwd ? p.fwd_qq : p.inv_qq);
+  return load_mulc(wu, qq, idx);
+}
+
+/*
+ * x[0..2^R) are the coefficients of one group: positions base + k*es of a block that starts stage s0.
+ * Forward: stages s0 .. s0+R-1; stage s0+u pairs x[k], x[k+d] with d = 2^(R-1-u); the 2^u sub-blocks use
+ * twiddle block index (blk0 << u) + sub.  Inverse: the same stages in the opposite order.
+ */
+template <int R, bool FWD, bool EXACT>
+__device__ __forceinline__ void radix_network(uint64_t (&x)[1 << R], const ntt_cuda_params_t &p, uint32_t s0,
+                                              uint32_t blk0)
+{
+  constexpr int n   = 1 << R;
+  const uint64_t c6 = 6 * p.q;
+  if(FWD) {
+#pragma unroll
+    for(int u = 0; u < R; u++) {
+      const int d = n >> (u + 1);
+#pragma unroll
+      for(int sub = 0; sub < (1 << u); sub++) {
+        const Mulc m = tw<EXACT>(p, true, s0 + u, (blk0 << u) + sub);
+#pragma unroll
+        for(int k = 0; k < d; k++) bfly_fwd<EXACT>(x[sub * 2 * d + k], x[sub * 2 * d + k + d], m, p, c6);
+      }
+    }
+  } else {
+#pragma unroll
+    for(int u = R - 1; u >= 0; u--) {
+      const int      d  = n >> (u + 1);
+      const uint32_t s  = s0 + u;
+      const uint64_t cb = p.inv_c[s];
+      /* renormalisation is only ever scheduled on the first stage a pass runs (u == R-1) */
+      if(!EXACT && u == R - 1 && ((p.inv_renorm_mask >> s) & 1u)) {
+        const Red rc{p.q, p.negq, p.red_shift, p.red_mu};
+#pragma unroll
+        for(int k = 0; k < n; k++) x[k] = reduce_3q(x[k], rc);
+      }
+      if(u == 0 && s == 0) {
+        /* global stage 0 (only reachable with blk0 == 0, u == 0): N^-1 folded in */
+        const Mulc a = mulc_from(p.ninv), b = mulc_from(p.ninv_w1);
+#pragma unroll
+        for(int k = 0; k < d; k++) bfly_inv_final<EXACT>(x[k], x[k + d], a, b, p, cb);
+      } else {
+#pragma unroll
+        for(int sub = 0; sub < (1 << u); sub++) {
+          const Mulc m = tw<EXACT>(p, false, s, (blk0 << u) + sub);
+#pragma unroll
+          for(int k = 0; k < d; k++) bfly_inv<EXACT>(x[sub * 2 * d + k], x[sub * 2 * d + k + d], m, p, cb);
+        }
+      }
+    }
+  }
+}
+
+template <bool EXACT>
+__device__ __forceinline__ uint64_t finish(uint64_t v, const ntt_cuda_params_t &p)
+{
+  if(EXACT) return csub(csub(v, p.q << 1), p.q);
+  const Red rc{p.q, p.negq, p.red_shift, p.red_mu};
+  return reduce_full(v, rc);
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* chunk kernel                                                                                      */
+/* ------------------------------------------------------------------------------------------------ */
+
+template <int L>
+struct ChunkCfg {
+  static constexpr int RC      = L < 4 ? L : 4;                     /* last pass: contiguous 2^RC per thread */
+  static constexpr int RB      = (L - RC) < 5 ? (L - RC) : 5;       /* middle pass */
+  static constexpr int RA      = L - RC - RB;                       /* first pass */
+  static constexpr int RMAX    = RA > RB ? (RA > RC ? RA : RC) : (RB > RC ? RB : RC);
+  static constexpr int GROUPS  = 1 << (L - RMAX);                   /* groups in the widest pass */
+  static constexpr int THREADS = GROUPS < 32 ? 32 : GROUPS;
+  /* resident CTAs per SM the register allocator should leave room for (128 registers per thread) */
+  static constexpr int MINB    = (512 / THREADS) < 16 ? (512 / THREADS) : 16;
+  static_assert(RA <= 5, "chunk too large");
+};
+
+/* One pass over the chunk in shared memory: local stages ls0 .. ls0+R-1 (forward order). */
+template <int L, int R, bool FWD, bool EXACT, bool FINISH, int THREADS>
+__device__ __forceinline__ void smem_pass(uint64_t *sm, const ntt_cuda_params_t &p, uint32_t ls0, uint32_t s1,
+                                          uint32_t chunk_in_poly)
+{
+  if(R == 0) return;
+  constexpr int n      = 1 << R;
+  constexpr int groups = 1 << (L - R);
+  const uint32_t es_log = L - ls0 - R; /* log2 of the element stride inside a group */
+  for(uint32_t g = threadIdx.x; g < (uint32_t)groups; g += THREADS) {
+    const uint32_t i    = g >> es_log;
+    const uint32_t j    = g & ((1u << es_log) - 1u);
+    const uint32_t base = (i << (L - ls0)) + j;
+    uint64_t       x[n];
+    if(R == 4 && ls0 + R == (uint32_t)L) {
+      /* contiguous 16 coefficients = one swizzled 128-byte row: eight 16-byte accesses */
+      const uint32_t row = base >> 4;
+#pragma unroll
+      for(int c = 0; c < 8; c++) {
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(sm + (row << 4) + (((uint32_t)c ^ (row & 7u)) << 1));
+        x[2 * c]           = v.x;
+        x[2 * c + 1]       = v.y;
+      }
+    } else {
+#pragma unroll
+      for(int k = 0; k < n; k++) x[k] = sm[swz(base + ((uint32_t)k << es_log))];
+    }
+    radix_network<R, FWD, EXACT>(x, p, s1 + ls0, (chunk_in_poly << ls0) + i);
+    if(FINISH) {
+#pragma unroll
+      for(int k = 0; k < n; k++) x[k] = finish<EXACT>(x[k], p);
+    }
+    if(R == 4 && ls0 + R == (uint32_t)L) {
+      const uint32_t row = base >> 4;
+#pragma unroll
+      for(int c = 0; c < 8; c++) {
+        ulonglong2 v;
+        v.x = x[2 * c];
+        v.y = x[2 * c + 1];
+        *reinterpret_cast<ulonglong2 *>(sm + (row << 4) + (((uint32_t)c ^ (row & 7u)) << 1)) = v;
+      }
+    } else {
+#pragma unroll
+      for(int k = 0; k < n; k++) sm[swz(base + ((uint32_t)k << es_log))] = x[k];
+    }
+  }
+}
+
+/*
+ * Forward: the chunk is block `chunk_in_poly` of global stage s1 (s1 = logn - L stages were already done by
+ * k_strided); runs local stages 0..L-1 and the final reduction.  Inverse: runs local stages L-1..0; if
+ * s1 == 0 that includes global stage 0 and the final reduction, otherwise values stay lazy for k_strided.
+ */
+template <int L, bool FWD, bool EXACT>
+__global__ void __launch_bounds__(ChunkCfg<L>::THREADS, ChunkCfg<L>::MINB) k_chunk(const __grid_constant__ ntt_cuda_params_t p,
+                                                                  uint64_t *__restrict__ a, size_t n_chunks)
+{
+  using C = ChunkCfg<L>;
+  extern __shared__ __align__(1024) uint64_t sm[];
+  constexpr uint32_t n   = 1u << L;
+  const uint32_t     s1  = p.logn - L;
+  constexpr int      T   = C::THREADS;
+
+  for(size_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    uint64_t *     g  = a + chunk * n;
+    const uint32_t cp = (uint32_t)(chunk & ((1u << s1) - 1u));
+
+    /* global -> shared, 16 bytes per access, swizzled */
+    if(L >= 1) {
+      for(uint32_t u = threadIdx.x; u < n / 2; u += T) {
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(g + 2 * u);
+        *reinterpret_cast<ulonglong2 *>(sm + 2 * (u ^ ((u >> 3) & 7u))) = v;
+      }
+    }
+    __syncthreads();
+
+    if(FWD) {
+      smem_pass<L, C::RA, true, EXACT, false, T>(sm, p, 0, s1, cp);
+      if(C::RA) __syncthreads();
+      smem_pass<L, C::RB, true, EXACT, false, T>(sm, p, C::RA, s1, cp);
+      if(C::RB) __syncthreads();
+      smem_pass<L, C::RC, true, EXACT, true, T>(sm, p, C::RA + C::RB, s1, cp);
+    } else {
+      if(s1 == 0) {
+        /* the pass that contains global stage 0 also applies the final reduction */
+        if(C::RA) {
+          smem_pass<L, C::RC, false, EXACT, false, T>(sm, p, C::RA + C::RB, s1, cp);
+          __syncthreads();
+          smem_pass<L, C::RB, false, EXACT, false, T>(sm, p, C::RA, s1, cp);
+          __syncthreads();
+          smem_pass<L, C::RA, false, EXACT, true, T>(sm, p, 0, s1, cp);
+        } else if(C::RB) {
+          smem_pass<L, C::RC, false, EXACT, false, T>(sm, p, C::RA + C::RB, s1, cp);
+          __syncthreads();
+          smem_pass<L, C::RB, false, EXACT, true, T>(sm, p, C::RA, s1, cp);
+        } else {
+          smem_pass<L, C::RC, false, EXACT, true, T>(sm, p, C::RA + C::RB, s1, cp);
+        }
+      } else {
+        smem_pass<L, C::RC, false, EXACT, false, T>(sm, p, C::RA + C::RB, s1, cp);
+        if(C::RB) __syncthreads();
+        smem_pass<L, C::RB, false, EXACT, false, T>(sm, p, C::RA, s1, cp);
+        if(C::RA) __syncthreads();
+        smem_pass<L, C::RA, false, EXACT, false, T>(sm, p, 0, s1, cp);
+      }
+    }
+    __syncthreads();
+
+    for(uint32_t u = threadIdx.x; u < n / 2; u += T) {
+      const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(sm + 2 * (u ^ ((u >> 3) & 7u)));
+      *reinterpret_cast<ulonglong2 *>(g + 2 * u) = v;
+    }
+    __syncthreads();
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* strided global pass                                                                               */
+/* ------------------------------------------------------------------------------------------------ */
+
+/*
+ * Global stages s0 .. s0+R-1 of every polynomial (forward order; the inverse runs them backwards).
+ * Thread <-> group g of a polynomial: es = N >> (s0+R), block i = g / es, offset j = g % es, coefficients
+ * at i*(es<<R) + j + k*es.  Consecutive threads have consecutive j, so each of the 2^R loads/stores of a
+ * warp covers 256 contiguous bytes.  FINISH applies the final reduction (inverse pass ending at stage 0).
+ */
+template <int R, bool FWD, bool EXACT, bool FINISH>
+__global__ void __launch_bounds__(256) k_strided(const __grid_constant__ ntt_cuda_params_t p,
+                                                 uint64_t *__restrict__ a, uint32_t s0, size_t total_groups)
+{
+  constexpr int  n      = 1 << R;
+  const uint32_t logn   = p.logn;
+  const uint32_t es_log = logn - s0 - R;
+  const uint32_t gl     = logn - R; /* log2 groups per polynomial */
+  for(size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total_groups;
+      t += (size_t)gridDim.x * blockDim.x) {
+    const size_t   poly = t >> gl;
+    const uint32_t g    = (uint32_t)(t & ((1u << gl) - 1u));
+    const uint32_t i    = g >> es_log;
+    const uint32_t j    = g & ((1u << es_log) - 1u);
+    uint64_t *     base = a + (poly << logn) + ((size_t)i << (logn - s0)) + j;
+    uint64_t       x[n];
+#pragma unroll
+    for(int k = 0; k < n; k++) x[k] = base[(size_t)k << es_log];
+    radix_network<R, FWD, EXACT>(x, p, s0, i);
+#pragma unroll
+    for(int k = 0; k < n; k++) base[(size_t)k << es_log] = FINISH ? finish<EXACT>(x[k], p) : x[k];
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* table generation                                                                                  */
+/* ------------------------------------------------------------------------------------------------ */
+
+typedef unsigned __int128 u128;
+
+__device__ __forceinline__ uint64_t mulmod128(uint64_t a, uint64_t b, uint64_t q)
+{
+  return (uint64_t)(((u128)a * b) % q);
+}
+
+/* d_w[bitrev_m(i)] = root^i mod q  (calc_w, pre_compute.h:38-51) -- one modpow per entry */
+__global__ void k_gen_roots(uint64_t *__restrict__ d_w, uint64_t root, uint32_t logn, uint64_t q)
+{
+  const uint64_t n = 1ull << logn;
+  for(uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t r = 1 % q, b = root % q, e = i;
+    while(e) {
+      if(e & 1) r = mulmod128(r, b, q);
+      b = mulmod128(b, b, q);
+      e >>= 1;
+    }
+    const uint64_t rev = logn ? (__brevll(i) >> (64 - logn)) : 0;
+    d_w[rev]           = r;
+  }
+}
+
+/* reference-format w[i] -> device multiplier (wu, qq) and, optionally, floor(w*2^64/q) (calc_w_con) */
+__global__ void k_build_tables(const uint64_t *__restrict__ d_w, uint4 *__restrict__ wu, uint2 *__restrict__ qq,
+                               uint64_t *__restrict__ con, uint64_t n, uint64_t q, int lazy)
+{
+  for(uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t w = d_w[i] % q;
+    const uint64_t c = (uint64_t)((((u128)w) << 64) / q);
+    if(con) con[i] = c;
+    if(lazy) {
+      const uint64_t u = (uint64_t)((((u128)w) << 32) % q);
+      wu[i]            = make_uint4((uint32_t)w, (uint32_t)(w >> 32), (uint32_t)u, (uint32_t)(u >> 32));
+      qq[i]            = make_uint2((uint32_t)((((u128)w) << 31) / q), (uint32_t)((((u128)u) << 31) / q));
+    } else {
+      wu[i] = make_uint4((uint32_t)w, (uint32_t)(w >> 32), (uint32_t)c, (uint32_t)(c >> 32));
+      qq[i] = make_uint2(0u, 0u);
+    }
+  }
+}
+
+/* c = a .* b mod q, exact for any q < 2^62 and inputs < 2^64 (128-bit product, Barrett by 2^128/q) */
+__global__ void k_pointwise(uint64_t *__restrict__ c, const uint64_t *__restrict__ a,
+                            const uint64_t *__restrict__ b, size_t n, uint64_t q, uint64_t mu_hi, uint64_t mu_lo)
+{
+  for(size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const uint64_t x = a[i], y = b[i];
+    const uint64_t ph = mulhi64(x, y), pl = x * y;
+    /* Q = floor(P * mu / 2^128) with mu = floor(2^128 / q) = mu_hi*2^64 + mu_lo; error <= 2 */
+    const uint64_t t1 = mulhi64(pl, mu_hi);
+    const uint64_t t2 = mulhi64(ph, mu_lo);
+    const uint64_t m  = ph * mu_hi; /* low 64 bits of ph*mu_hi: P < q*2^64 keeps Q below 2^64 */
+    uint64_t       Q  = m + t1 + t2;
+    uint64_t       r  = pl - Q * q;
+    r                 = csub(r, q << 1);
+    r                 = csub(r, q);
+    /* cross-term carries can leave one more q */
+    r    = csub(r, q);
+    c[i] = r;
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* launchers                                                                                         */
+/* ------------------------------------------------------------------------------------------------ */
+
+struct DevGuard {
+  int prev = -1;
+  bool ok  = true;
+  explicit DevGuard(int dev)
+  {
+    if(cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if(prev != dev) ok = (cudaSetDevice(dev) == cudaSuccess);
+  }
+  ~DevGuard()
+  {
+    if(prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+static int sm_count(int device)
+{
+  static int cache[64];
+  if(device < 0 || device >= 64) return 148;
+  if(!cache[device]) {
+    int n = 0;
+    if(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || n <= 0) n = 148;
+    cache[device] = n;
+  }
+  return cache[device];
+}
+
+extern "C" int ntt_cuda_malloc(int device, void **d_ptr, size_t bytes)
+{
+  DevGuard g(device);
+  if(!g.ok) return fail_msg("cudaSetDevice failed");
+  CU(cudaMalloc(d_ptr, bytes ? bytes : 1));
+  return 0;
+}
+extern "C" int ntt_cuda_free(int device, void *d_ptr)
+{
+  DevGuard g(device);
+  if(!g.ok) return fail_msg("cudaSetDevice failed");
+  CU(cudaFree(d_ptr));
+  return 0;
+}
+extern "C" int ntt_cuda_host_alloc(void **h_ptr, size_t bytes)
+{
+  CU(cudaHostAlloc(h_ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+  return 0;
+}
+extern "C" int ntt_cuda_host_free(void *h_ptr)
+{
+  CU(cudaFreeHost(h_ptr));
+  return 0;
+}
+extern "C" int ntt_cuda_h2d(int device, void *d_dst, const void *h_src, size_t bytes, void *stream)
+{
+  DevGuard g(device);
+  if(!g.ok) return fail_msg("cudaSetDevice failed");
+  CU(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return 0;
+}
+extern "C" int ntt_cuda_d2h(int device, void *h_dst, const void *d_src, size_t bytes, void *stream)
+{
+  DevGuard g(device);
+  if(!g.ok) return fail_msg("cudaSetDevice failed");
+  CU(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return 0;
+}
+extern "C" int ntt_cuda_sync(int device, void *stream)
+{
+  DevGuard g(device);
+  if(!g.ok) return fail_msg("cudaSetDevice failed");
+  if(stream) {
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+  } else {
+    CU(cudaDeviceSynchronize());
+  }
+  return 0;
+}
+extern "C" int ntt_cuda_stream_create(int device, void **stream)
+{
+  DevGuard g(device);
+  if(!g.ok) return fail_msg("cudaSetDevice failed");
+  cudaStream_t s;
+  CU(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  *stream = (void *)s;
+  return 0;
+}
+extern "C" int ntt_cuda_stream_destroy(int device, void *stream)
+{
+  DevGuard g(device);
+  if(!g.ok) return fail_msg("cudaSetDevice failed");
+  CU(cudaStreamDestroy((cudaStream_t)stream));
+  return 0;
+}
+
+extern "C" int ntt_cuda_gen_root_table(int device, uint64_t *d_w, uint64_t root, uint64_t N, uint64_t q,
+                                       void *stream)
+{
+  DevGuard g(device);
+  if(!g.ok) return fail_msg("cudaSetDevice failed");
+  uint32_t logn = 0;
+  while((1ull << logn) < N) logn++;
+  const int blocks = (int)((N + 255) / 256 < 4096 ? (N + 255) / 256 : 4096);
+  k_gen_roots<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_w, root, logn, q);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ntt_cuda_build_tables(int device, const ntt_cuda_params_t *p, const uint64_t *d_w, void *d_wu,
+                                     void *d_qq, uint64_t *d_con_out, uint64_t N, void *stream)
+{
+  DevGuard g(device);
+  if(!g.ok) return fail_msg("cudaSetDevice failed");
+  const int blocks = (int)((N + 255) / 256 < 4096 ? (N + 255) / 256 : 4096);
+  k_build_tables<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_w, (uint4 *)d_wu, (uint2 *)d_qq, d_con_out, N, p->q,
+                                                          (int)p->lazy);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+/* ---- transform dispatch ---------------------------------------------------------------------------- */
+
+template <int L, bool FWD, bool EXACT>
+static int launch_chunk(int device, const ntt_cuda_params_t &p, uint64_t *d_a, size_t n_chunks, cudaStream_t st)
+{
+  using C            = ChunkCfg<L>;
+  const size_t smem  = (size_t)8 << L;
+  auto         kern  = k_chunk<L, FWD, EXACT>;
+  static bool  ready[64] = {false};
+  if(!ready[device & 63]) {
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ready[device & 63] = true;
+  }
+  int per_sm = 1;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::THREADS, smem));
+  if(per_sm < 1) per_sm = 1;
+  size_t grid = (size_t)sm_count(device) * per_sm;
+  if(grid > n_chunks) grid = n_chunks;
+  kern<<<(unsigned)grid, C::THREADS, smem, st>>>(p, d_a, n_chunks);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+template <bool FWD, bool EXACT>
+static int dispatch_chunk(int device, int L, const ntt_cuda_params_t &p, uint64_t *d_a, size_t n_chunks,
+                          cudaStream_t st)
+{
+  switch(L) {
+#define CASE(l) \
+  case l: return launch_chunk<l, FWD, EXACT>(device, p, d_a, n_chunks, st);
+    CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13)
+    CASE(14)
+#undef CASE
+    default: return fail_msg("unsupported chunk size");
+  }
+}
+
+template <int R, bool FWD, bool EXACT, bool FINISH>
+static int launch_strided(int device, const ntt_cuda_params_t &p, uint64_t *d_a, uint32_t s0, size_t batch,
+                          cudaStream_t st)
+{
+  const size_t total = batch << (p.logn - R);
+  size_t       grid  = (total + 255) / 256;
+  const size_t cap   = (size_t)sm_count(device) * 32;
+  if(grid > cap) grid = cap;
+  k_strided<R, FWD, EXACT, FINISH><<<(unsigned)grid, 256, 0, st>>>(p, d_a, s0, total);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+template <bool FWD, bool EXACT, bool FINISH>
+static int dispatch_strided(int device, int R, const ntt_cuda_params_t &p, uint64_t *d_a, uint32_t s0,
+                            size_t batch, cudaStream_t st)
+{
+  switch(R) {
+    case 1: return launch_strided<1, FWD, EXACT, FINISH>(device, p, d_a, s0, batch, st);
+    case 2: return launch_strided<2, FWD, EXACT, FINISH>(device, p, d_a, s0, batch, st);
+    case 3: return launch_strided<3, FWD, EXACT, FINISH>(device, p, d_a, s0, batch, st);
+    case 4: return launch_strided<4, FWD, EXACT, FINISH>(device, p, d_a, s0, batch, st);
+    case 5: return launch_strided<5, FWD, EXACT, FINISH>(device, p, d_a, s0, batch, st);
+    default: return fail_msg("unsupported strided radix");
+  }
+}
+
+/* How the stages of a 2^logn transform are split: `ns` strided passes of radix 2^r[i] cover the first
+ * S1 = sum r[i] stages, the chunk kernel covers the remaining L = logn - S1 (<= 14). */
+struct Split {
+  int L;
+  int ns;
+  int r[4];
+};
+static Split make_split(int logn)
+{
+  Split s{};
+  int   rest = logn > 14 ? logn - 14 : 0; /* stages that do not fit a chunk */
+  s.L        = logn - rest;
+  s.ns       = 0;
+  while(rest > 0) {
+    /* balanced radices, at most 2^5 per pass */
+    const int passes = (rest + 4) / 5;
+    const int r      = (rest + passes - 1) / passes;
+    s.r[s.ns++]      = r;
+    rest -= r;
+  }
+  return s;
+}
+
+/* Inverse lazy bookkeeping (see ntt_cuda.h): walks the passes in the order the inverse runs them and
+ * records, per global stage s, the bound constant inv_c[s] = B_s*q and where values must first be pulled
+ * back below 3q so that neither x+y nor x-y+B_s*q can reach 2^63. */
+extern "C" int ntt_cuda_plan_inverse_bounds(ntt_cuda_params_t *p)
+{
+  const int logn = (int)p->logn;
+  if(logn < 1 || logn > NTT_MAX_STAGES) return fail_msg("logn out of range");
+  memset(p->inv_c, 0, sizeof(p->inv_c));
+  p->inv_renorm_mask = 0;
+  const Split sp     = make_split(logn);
+  int         s1     = 0;
+  for(int k = 0; k < sp.ns; k++) s1 += sp.r[k];
+  /* (top stage, radix) of every pass in inverse processing order */
+  int tops[8], rads[8], np = 0;
+  {
+    const int L  = sp.L;
+    const int RC = L < 4 ? L : 4, RB = (L - RC) < 5 ? (L - RC) : 5, RA = L - RC - RB;
+    if(RC) { tops[np] = s1 + L - 1; rads[np++] = RC; }
+    if(RB) { tops[np] = s1 + RA + RB - 1; rads[np++] = RB; }
+    if(RA) { tops[np] = s1 + RA - 1; rads[np++] = RA; }
+    int s0 = s1;
+    for(int k = sp.ns - 1; k >= 0; k--) {
+      s0 -= sp.r[k];
+      tops[np]   = s0 + sp.r[k] - 1;
+      rads[np++] = sp.r[k];
+    }
+  }
+  const long double lim = 9223372036854775808.0L; /* 2^63 */
+  long double       B   = 2.0L;                   /* input contract of the inverse: [0,2q) */
+  for(int k = 0; k < np; k++) {
+    if(B * (long double)(1u << rads[k]) * (long double)p->q >= lim) {
+      p->inv_renorm_mask |= 1u << tops[k];
+      B = 3.0L;
+    }
+    if(B * (long double)(1u << rads[k]) * (long double)p->q >= lim) return fail_msg("q too large for the lazy inverse");
+    for(int u = 0; u < rads[k]; u++) {
+      const int s = tops[k] - u;
+      p->inv_c[s] = (uint64_t)B * p->q;
+      B           = (2 * B > 6.0L) ? 2 * B : 6.0L;
+    }
+  }
+  return 0;
+}
+
+template <bool EXACT>
+static int forward_impl(int device, const ntt_cuda_params_t &p, uint64_t *d_a, size_t batch, cudaStream_t st)
+{
+  const Split sp = make_split((int)p.logn);
+  uint32_t    s0 = 0;
+  for(int k = 0; k < sp.ns; k++) {
+    if(dispatch_strided<true, EXACT, false>(device, sp.r[k], p, d_a, s0, batch, st)) return -1;
+    s0 += sp.r[k];
+  }
+  return dispatch_chunk<true, EXACT>(device, sp.L, p, d_a, batch << s0, st);
+}
+
+template <bool EXACT>
+static int inverse_impl(int device, const ntt_cuda_params_t &p, uint64_t *d_a, size_t batch, cudaStream_t st)
+{
+  const Split sp = make_split((int)p.logn);
+  uint32_t    s1 = 0;
+  for(int k = 0; k < sp.ns; k++) s1 += sp.r[k];
+  if(dispatch_chunk<false, EXACT>(device, sp.L, p, d_a, batch << s1, st)) return -1;
+  uint32_t s0 = s1;
+  for(int k = sp.ns - 1; k >= 0; k--) {
+    s0 -= sp.r[k];
+    const int rc = (k == 0) ? dispatch_strided<false, EXACT, true>(device, sp.r[k], p, d_a, s0, batch, st)
+                            : dispatch_strided<false, EXACT, false>(device, sp.r[k], p, d_a, s0, batch, st);
+    if(rc) return -1;
+  }
+  return 0;
+}
+
+extern "C" int ntt_cuda_forward(int device, const ntt_cuda_params_t *p, uint64_t *d_a, size_t batch, void *stream)
+{
+  if(batch == 0) return 0;
+  DevGuard g(device);
+  if(!g.ok) return fail_msg("cudaSetDevice failed");
+  if(p->logn < 1 || p->logn > NTT_MAX_STAGES) return fail_msg("logn out of range");
+  return p->lazy ? forward_impl<false>(device, *p, d_a, batch, (cudaStream_t)stream)
+                 : forward_impl<true>(device, *p, d_a, batch, (cudaStream_t)stream);
+}
+
+extern "C" int ntt_cuda_inverse(int device, const ntt_cuda_params_t *p, uint64_t *d_a, size_t batch, void *stream)
+{
+  if(batch == 0) return 0;
+  DevGuard g(device);
+  if(!g.ok) return fail_msg("cudaSetDevice failed");
+  if(p->logn < 1 || p->logn > NTT_MAX_STAGES) return fail_msg("logn out of range");
+  return p->lazy ? inverse_impl<false>(device, *p, d_a, batch, (cudaStream_t)stream)
+                 : inverse_impl<true>(device, *p, d_a, batch, (cudaStream_t)stream);
+}
+
+extern "C" int ntt_cuda_pointwise(int device, const ntt_cuda_params_t *p, uint64_t *d_c, const uint64_t *d_a,
+                                  const uint64_t *d_b, size_t n, void *stream)
+{
+  if(n == 0) return 0;
+  DevGuard g(device);
+  if(!g.ok) return fail_msg("cudaSetDevice failed");
+  /* mu = floor(2^128 / q) via two 128/64 divisions on the host */
+  const u128     top  = ~(u128)0;
+  u128           mu   = top / p->q; /* floor((2^128-1)/q) == floor(2^128/q) for q not a power of two */
+  const uint64_t mu_hi = (uint64_t)(mu >> 64), mu_lo = (uint64_t)mu;
+  size_t         grid  = (n + 255) / 256;
+  const size_t   cap   = (size_t)sm_count(device) * 16;
+  if(grid > cap) grid = cap;
+  k_pointwise<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(d_c, d_a, d_b, n, p->q, mu_hi, mu_lo);
+  CU(cudaGetLastError());
+  return 0;
+}

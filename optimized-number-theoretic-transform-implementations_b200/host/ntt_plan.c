@@ -1,0 +1,504 @@
+/*
+ * host/ntt_plan.c -- the C host side of libntt_b200: plans, batch entry points, host-buffer pipeline.
+ *
+ * Mirrors the reference's operator interface for the NTT hot path (include/ntt_reference.h:13-65): same
+ * argument meaning, in-place transforms, caller-owned buffers, SUCCESS 0 / ERROR -1
+ * (include/internal/defs.h:20-21).  All arithmetic on coefficients happens in the CUDA layer
+ * (csrc/ntt_kernels.cu); there is no CPU implementation of the transform in this library.
+ */
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/ntt_b200.h"
+#include "../csrc/ntt_cuda.h"
+#include "ntt_math.h"
+
+typedef unsigned __int128 u128;
+
+#define LAZY_MAX_QBITS 56 /* lazy path needs (4 + 6*24) * q < 2^64 */
+#define HOST_PIPE_DEPTH 3
+#define HOST_PIPE_BYTES ((size_t)32 << 20)
+
+struct ntt_b200_plan {
+  int      device;
+  uint64_t N, q;
+  unsigned logn;
+  int      has_fwd, has_inv;
+  uint64_t n_inv, n_inv_con;
+  ntt_cuda_params_t params;
+  /* device memory: kernel tables and the reference-format copies kept for export */
+  void *    d_fwd_wu, *d_fwd_qq, *d_inv_wu, *d_inv_qq;
+  uint64_t *d_w, *d_w_con, *d_w_inv, *d_w_inv_con;
+  /* host-buffer pipeline (created on first use) */
+  pthread_mutex_t pipe_lock;
+  void *          pipe_stream[HOST_PIPE_DEPTH];
+  uint64_t *      pipe_buf[HOST_PIPE_DEPTH];
+  size_t          pipe_polys;
+};
+
+static __thread char g_error[512];
+
+static int set_error(const char *fmt, const char *detail)
+{
+  snprintf(g_error, sizeof(g_error), fmt, detail ? detail : "");
+  return NTT_B200_ERROR;
+}
+static int cuda_error(const char *where)
+{
+  snprintf(g_error, sizeof(g_error), "%s: %s", where, ntt_cuda_error());
+  return NTT_B200_ERROR;
+}
+
+const char *ntt_b200_last_error(void) { return g_error; }
+int         ntt_b200_device_count(void) { return ntt_cuda_device_count(); }
+const char *ntt_b200_version(void) { return "ntt_b200 0.1 sm_100a"; }
+
+/* ---- multiplier constants ------------------------------------------------------------------------ */
+
+static ntt_cuda_mulc_t make_mulc(uint64_t w, uint64_t q, int lazy)
+{
+  ntt_cuda_mulc_t m;
+  memset(&m, 0, sizeof(m));
+  w %= q;
+  m.w0 = (uint32_t)w;
+  m.w1 = (uint32_t)(w >> 32);
+  if(lazy) {
+    const uint64_t u = (uint64_t)((((u128)w) << 32) % q);
+    m.u0             = (uint32_t)u;
+    m.u1             = (uint32_t)(u >> 32);
+    m.wq             = (uint32_t)nttm_shoup(w, q, 31);
+    m.uq             = (uint32_t)nttm_shoup(u, q, 31);
+  } else {
+    const uint64_t c = nttm_shoup(w, q, 64);
+    m.u0             = (uint32_t)c;
+    m.u1             = (uint32_t)(c >> 32);
+  }
+  return m;
+}
+
+static int check_shape(uint64_t N, uint64_t q, int device)
+{
+  if(N < 2 || (N & (N - 1)) != 0 || nttm_log2(N) > NTT_B200_MAX_LOGN)
+    return set_error("N must be a power of two in [2, 2^24]%s", NULL);
+  if(q < 3 || (q & 1) == 0 || (q >> 62) != 0) return set_error("q must be odd and 3 <= q < 2^62%s", NULL);
+  const int ndev = ntt_cuda_device_count();
+  if(ndev <= 0) return set_error("no CUDA device available (this library has no CPU fallback)%s", NULL);
+  if(device < 0 || device >= ndev) return set_error("device index out of range%s", NULL);
+  return NTT_B200_SUCCESS;
+}
+
+static void fill_params(ntt_b200_plan_t *pl)
+{
+  ntt_cuda_params_t *p = &pl->params;
+  memset(p, 0, sizeof(*p));
+  p->q         = pl->q;
+  p->neg2q     = (uint64_t)0 - 2 * pl->q;
+  p->negq      = (uint64_t)0 - pl->q;
+  p->logn      = pl->logn;
+  p->lazy      = nttm_bitlen(pl->q) <= LAZY_MAX_QBITS ? 1u : 0u;
+  p->red_shift = nttm_bitlen(pl->q) - 1;
+  p->red_mu    = (uint32_t)((((u128)1) << (32 + p->red_shift)) / pl->q);
+}
+
+static void plan_free(ntt_b200_plan_t *pl)
+{
+  if(!pl) return;
+  void *dev_ptrs[] = {pl->d_fwd_wu, pl->d_fwd_qq, pl->d_inv_wu, pl->d_inv_qq,
+                      pl->d_w,      pl->d_w_con,  pl->d_w_inv,  pl->d_w_inv_con};
+  for(size_t i = 0; i < sizeof(dev_ptrs) / sizeof(dev_ptrs[0]); i++) {
+    if(dev_ptrs[i]) ntt_cuda_free(pl->device, dev_ptrs[i]);
+  }
+  for(int i = 0; i < HOST_PIPE_DEPTH; i++) {
+    if(pl->pipe_buf[i]) ntt_cuda_free(pl->device, pl->pipe_buf[i]);
+    if(pl->pipe_stream[i]) ntt_cuda_stream_destroy(pl->device, pl->pipe_stream[i]);
+  }
+  pthread_mutex_destroy(&pl->pipe_lock);
+  free(pl);
+}
+
+static ntt_b200_plan_t *plan_alloc(int device, uint64_t N, uint64_t q)
+{
+  ntt_b200_plan_t *pl = calloc(1, sizeof(*pl));
+  if(!pl) return NULL;
+  pl->device = device;
+  pl->N      = N;
+  pl->q      = q;
+  pl->logn   = nttm_log2(N);
+  pthread_mutex_init(&pl->pipe_lock, NULL);
+  fill_params(pl);
+  return pl;
+}
+
+/* d_w (reference format, on device) -> kernel tables + companion table */
+static int build_direction(ntt_b200_plan_t *pl, const uint64_t *d_w, void **wu, void **qq, uint64_t **con)
+{
+  const size_t n = (size_t)pl->N;
+  if(ntt_cuda_malloc(pl->device, wu, n * 16)) return cuda_error("table alloc");
+  if(ntt_cuda_malloc(pl->device, qq, n * 8)) return cuda_error("table alloc");
+  if(ntt_cuda_malloc(pl->device, (void **)con, n * 8)) return cuda_error("table alloc");
+  if(ntt_cuda_build_tables(pl->device, &pl->params, d_w, *wu, *qq, *con, pl->N, NULL))
+    return cuda_error("table build");
+  return NTT_B200_SUCCESS;
+}
+
+static int finish_inverse_constants(ntt_b200_plan_t *pl, uint64_t w_inv_1)
+{
+  const int lazy      = (int)pl->params.lazy;
+  pl->params.ninv     = make_mulc(pl->n_inv, pl->q, lazy);
+  pl->params.ninv_w1  = make_mulc(nttm_mulmod(pl->n_inv % pl->q, w_inv_1 % pl->q, pl->q), pl->q, lazy);
+  if(lazy && ntt_cuda_plan_inverse_bounds(&pl->params)) return cuda_error("inverse bounds");
+  return NTT_B200_SUCCESS;
+}
+
+/* upload one reference table, build the kernel tables, verify the caller's companion table */
+static int adopt_table(ntt_b200_plan_t *pl, const uint64_t *w, const uint64_t *w_con, uint64_t **d_w, void **wu,
+                       void **qq, uint64_t **d_con, const char *name)
+{
+  const size_t bytes = (size_t)pl->N * 8;
+  if(ntt_cuda_malloc(pl->device, (void **)d_w, bytes)) return cuda_error("table alloc");
+  if(ntt_cuda_h2d(pl->device, *d_w, w, bytes, NULL)) return cuda_error("table upload");
+  int rc = build_direction(pl, *d_w, wu, qq, d_con);
+  if(rc) return rc;
+  if(w_con) {
+    uint64_t *chk = malloc(bytes);
+    if(!chk) return set_error("out of host memory%s", NULL);
+    rc = ntt_cuda_d2h(pl->device, chk, *d_con, bytes, NULL) || ntt_cuda_sync(pl->device, NULL);
+    if(rc) {
+      free(chk);
+      return cuda_error("table download");
+    }
+    /* entry 0 (w = 1) is never used by the transform (src/ntt_reference.c:19-22 starts at m = 1) */
+    const int same = memcmp(chk + 1, w_con + 1, bytes - 8) == 0;
+    free(chk);
+    if(!same) return set_error("%s does not equal floor(w * 2^64 / q): tables inconsistent with q", name);
+  } else if(ntt_cuda_sync(pl->device, NULL)) {
+    return cuda_error("table build");
+  }
+  return NTT_B200_SUCCESS;
+}
+
+int ntt_b200_plan_create(ntt_b200_plan_t **plan, int device, uint64_t N, uint64_t q, const uint64_t *w,
+                         const uint64_t *w_con, const uint64_t *w_inv, const uint64_t *w_inv_con, uint64_t n_inv,
+                         uint64_t n_inv_con)
+{
+  if(!plan) return set_error("plan pointer is NULL%s", NULL);
+  *plan = NULL;
+  if(check_shape(N, q, device)) return NTT_B200_ERROR;
+  if(!w && !w_inv) return set_error("at least one of w / w_inv must be given%s", NULL);
+  ntt_b200_plan_t *pl = plan_alloc(device, N, q);
+  if(!pl) return set_error("out of host memory%s", NULL);
+  int rc = NTT_B200_SUCCESS;
+  if(w) {
+    rc = adopt_table(pl, w, w_con, &pl->d_w, &pl->d_fwd_wu, &pl->d_fwd_qq, &pl->d_w_con, "w_con");
+    pl->has_fwd = (rc == NTT_B200_SUCCESS);
+  }
+  if(!rc && w_inv) {
+    if(nttm_mulmod(n_inv % q, N % q, q) != 1 % q) {
+      rc = set_error("n_inv is not N^-1 mod q%s", NULL);
+    } else if(n_inv_con != nttm_shoup(n_inv, q, 64)) {
+      rc = set_error("n_inv_con does not equal floor(n_inv * 2^64 / q)%s", NULL);
+    } else {
+      rc = adopt_table(pl, w_inv, w_inv_con, &pl->d_w_inv, &pl->d_inv_wu, &pl->d_inv_qq, &pl->d_w_inv_con,
+                       "w_inv_con");
+    }
+    if(!rc) {
+      pl->n_inv     = n_inv;
+      pl->n_inv_con = n_inv_con;
+      rc            = finish_inverse_constants(pl, w_inv[1]);
+      pl->has_inv   = (rc == NTT_B200_SUCCESS);
+    }
+  }
+  if(rc) {
+    plan_free(pl);
+    return rc;
+  }
+  pl->params.fwd_wu = pl->d_fwd_wu;
+  pl->params.fwd_qq = pl->d_fwd_qq;
+  pl->params.inv_wu = pl->d_inv_wu;
+  pl->params.inv_qq = pl->d_inv_qq;
+  *plan             = pl;
+  return NTT_B200_SUCCESS;
+}
+
+int ntt_b200_plan_create_psi(ntt_b200_plan_t **plan, int device, uint64_t N, uint64_t q, uint64_t psi)
+{
+  if(!plan) return set_error("plan pointer is NULL%s", NULL);
+  *plan = NULL;
+  if(check_shape(N, q, device)) return NTT_B200_ERROR;
+  psi %= q;
+  if(nttm_powmod(psi, N, q) != q - 1) return set_error("psi is not a primitive 2N-th root of unity mod q%s", NULL);
+  ntt_b200_plan_t *pl = plan_alloc(device, N, q);
+  if(!pl) return set_error("out of host memory%s", NULL);
+  const uint64_t psi_inv = nttm_powmod(psi, 2 * N - 1, q);
+  /* N^-1 = ((q+1)/2)^log2(N): valid for any odd q */
+  pl->n_inv     = nttm_powmod((q + 1) / 2, pl->logn, q);
+  pl->n_inv_con = nttm_shoup(pl->n_inv, q, 64);
+  const size_t bytes = (size_t)N * 8;
+  int          rc    = NTT_B200_SUCCESS;
+  if(ntt_cuda_malloc(device, (void **)&pl->d_w, bytes) || ntt_cuda_malloc(device, (void **)&pl->d_w_inv, bytes)) {
+    rc = cuda_error("table alloc");
+  } else if(ntt_cuda_gen_root_table(device, pl->d_w, psi, N, q, NULL) ||
+            ntt_cuda_gen_root_table(device, pl->d_w_inv, psi_inv, N, q, NULL)) {
+    rc = cuda_error("table generation");
+  }
+  if(!rc) rc = build_direction(pl, pl->d_w, &pl->d_fwd_wu, &pl->d_fwd_qq, &pl->d_w_con);
+  if(!rc) rc = build_direction(pl, pl->d_w_inv, &pl->d_inv_wu, &pl->d_inv_qq, &pl->d_w_inv_con);
+  if(!rc && ntt_cuda_sync(device, NULL)) rc = cuda_error("table generation");
+  /* w_inv[1] = psi_inv^(N/2) */
+  if(!rc) rc = finish_inverse_constants(pl, nttm_powmod(psi_inv, N / 2, q));
+  if(rc) {
+    plan_free(pl);
+    return rc;
+  }
+  pl->has_fwd = pl->has_inv = 1;
+  pl->params.fwd_wu = pl->d_fwd_wu;
+  pl->params.fwd_qq = pl->d_fwd_qq;
+  pl->params.inv_wu = pl->d_inv_wu;
+  pl->params.inv_qq = pl->d_inv_qq;
+  *plan             = pl;
+  return NTT_B200_SUCCESS;
+}
+
+int ntt_b200_plan_destroy(ntt_b200_plan_t *plan)
+{
+  plan_free(plan);
+  return NTT_B200_SUCCESS;
+}
+
+uint64_t ntt_b200_plan_n(const ntt_b200_plan_t *plan) { return plan ? plan->N : 0; }
+uint64_t ntt_b200_plan_q(const ntt_b200_plan_t *plan) { return plan ? plan->q : 0; }
+int      ntt_b200_plan_device(const ntt_b200_plan_t *plan) { return plan ? plan->device : -1; }
+int      ntt_b200_plan_is_lazy(const ntt_b200_plan_t *plan) { return plan ? (int)plan->params.lazy : 0; }
+
+int ntt_b200_plan_export_tables(const ntt_b200_plan_t *plan, uint64_t *w, uint64_t *w_con, uint64_t *w_inv,
+                                uint64_t *w_inv_con, uint64_t *n_inv, uint64_t *n_inv_con)
+{
+  if(!plan) return set_error("plan is NULL%s", NULL);
+  const size_t bytes = (size_t)plan->N * 8;
+  struct {
+    uint64_t *      dst;
+    const uint64_t *src;
+  } jobs[4] = {{w, plan->d_w}, {w_con, plan->d_w_con}, {w_inv, plan->d_w_inv}, {w_inv_con, plan->d_w_inv_con}};
+  for(int i = 0; i < 4; i++) {
+    if(!jobs[i].dst) continue;
+    if(!jobs[i].src) return set_error("plan does not hold the requested table%s", NULL);
+    if(ntt_cuda_d2h(plan->device, jobs[i].dst, jobs[i].src, bytes, NULL)) return cuda_error("table download");
+  }
+  if(ntt_cuda_sync(plan->device, NULL)) return cuda_error("table download");
+  if(n_inv) *n_inv = plan->n_inv;
+  if(n_inv_con) *n_inv_con = plan->n_inv_con;
+  return NTT_B200_SUCCESS;
+}
+
+/* ---- device-resident batches --------------------------------------------------------------------- */
+
+static int check_batch(const ntt_b200_plan_t *plan, const void *d_a, int need_inv)
+{
+  if(!plan) return set_error("plan is NULL%s", NULL);
+  if(!d_a) return set_error("data pointer is NULL%s", NULL);
+  if(((uintptr_t)d_a & 15) != 0) return set_error("device data must be 16-byte aligned%s", NULL);
+  if(need_inv ? !plan->has_inv : !plan->has_fwd)
+    return set_error("plan was created without the %s tables", need_inv ? "inverse" : "forward");
+  return NTT_B200_SUCCESS;
+}
+
+int ntt_b200_fwd_batch(const ntt_b200_plan_t *plan, uint64_t *d_a, size_t batch, void *stream)
+{
+  if(check_batch(plan, d_a, 0)) return NTT_B200_ERROR;
+  if(ntt_cuda_forward(plan->device, &plan->params, d_a, batch, stream)) return cuda_error("forward NTT");
+  return NTT_B200_SUCCESS;
+}
+
+int ntt_b200_fwd_lazy_batch(const ntt_b200_plan_t *plan, uint64_t *d_a, size_t batch, void *stream)
+{
+  /* [0,q) is a valid lazy representative of the reference's [0,4q) contract */
+  return ntt_b200_fwd_batch(plan, d_a, batch, stream);
+}
+
+int ntt_b200_inv_batch(const ntt_b200_plan_t *plan, uint64_t *d_a, size_t batch, void *stream)
+{
+  if(check_batch(plan, d_a, 1)) return NTT_B200_ERROR;
+  if(ntt_cuda_inverse(plan->device, &plan->params, d_a, batch, stream)) return cuda_error("inverse NTT");
+  return NTT_B200_SUCCESS;
+}
+
+static int rns_apply(ntt_b200_plan_t *const *plans, size_t limbs, uint64_t *d_a, size_t batch_per_limb,
+                     void *stream, int inverse)
+{
+  if(!plans || limbs == 0) return set_error("no plans given%s", NULL);
+  for(size_t l = 0; l < limbs; l++) {
+    if(!plans[l] || plans[l]->N != plans[0]->N || plans[l]->device != plans[0]->device)
+      return set_error("RNS plans must share N and device%s", NULL);
+  }
+  const size_t limb_words = batch_per_limb * (size_t)plans[0]->N;
+  for(size_t l = 0; l < limbs; l++) {
+    const int rc = inverse ? ntt_b200_inv_batch(plans[l], d_a + l * limb_words, batch_per_limb, stream)
+                           : ntt_b200_fwd_batch(plans[l], d_a + l * limb_words, batch_per_limb, stream);
+    if(rc) return rc;
+  }
+  return NTT_B200_SUCCESS;
+}
+
+int ntt_b200_fwd_rns(ntt_b200_plan_t *const *plans, size_t limbs, uint64_t *d_a, size_t batch_per_limb,
+                     void *stream)
+{
+  return rns_apply(plans, limbs, d_a, batch_per_limb, stream, 0);
+}
+int ntt_b200_inv_rns(ntt_b200_plan_t *const *plans, size_t limbs, uint64_t *d_a, size_t batch_per_limb,
+                     void *stream)
+{
+  return rns_apply(plans, limbs, d_a, batch_per_limb, stream, 1);
+}
+
+int ntt_b200_pointwise_mul_batch(const ntt_b200_plan_t *plan, uint64_t *d_c, const uint64_t *d_a,
+                                 const uint64_t *d_b, size_t batch, void *stream)
+{
+  if(!plan || !d_c || !d_a || !d_b) return set_error("NULL argument%s", NULL);
+  if(ntt_cuda_pointwise(plan->device, &plan->params, d_c, d_a, d_b, batch * (size_t)plan->N, stream))
+    return cuda_error("pointwise product");
+  return NTT_B200_SUCCESS;
+}
+
+int ntt_b200_negacyclic_mul_batch(const ntt_b200_plan_t *plan, uint64_t *d_c, uint64_t *d_a, uint64_t *d_b,
+                                  size_t batch, void *stream)
+{
+  if(check_batch(plan, d_a, 1) || check_batch(plan, d_b, 0) || check_batch(plan, d_c, 0)) return NTT_B200_ERROR;
+  if(ntt_b200_fwd_batch(plan, d_a, batch, stream)) return NTT_B200_ERROR;
+  if(ntt_b200_fwd_batch(plan, d_b, batch, stream)) return NTT_B200_ERROR;
+  if(ntt_b200_pointwise_mul_batch(plan, d_c, d_a, d_b, batch, stream)) return NTT_B200_ERROR;
+  return ntt_b200_inv_batch(plan, d_c, batch, stream);
+}
+
+/* ---- host-resident batches ------------------------------------------------------------------------- */
+
+static int pipe_prepare(ntt_b200_plan_t *pl)
+{
+  if(pl->pipe_polys) return NTT_B200_SUCCESS;
+  const size_t poly_bytes = (size_t)pl->N * 8;
+  size_t       polys      = HOST_PIPE_BYTES / poly_bytes;
+  if(polys < 1) polys = 1;
+  for(int i = 0; i < HOST_PIPE_DEPTH; i++) {
+    if(ntt_cuda_stream_create(pl->device, &pl->pipe_stream[i])) return cuda_error("stream create");
+    if(ntt_cuda_malloc(pl->device, (void **)&pl->pipe_buf[i], polys * poly_bytes)) return cuda_error("staging alloc");
+  }
+  pl->pipe_polys = polys;
+  return NTT_B200_SUCCESS;
+}
+
+/* H2D -> transform -> D2H in chunks, HOST_PIPE_DEPTH chunks in flight on their own streams */
+static int host_apply(const ntt_b200_plan_t *plan, uint64_t *h_a, size_t batch, int inverse)
+{
+  if(!plan) return set_error("plan is NULL%s", NULL);
+  if(!h_a) return set_error("data pointer is NULL%s", NULL);
+  if(inverse ? !plan->has_inv : !plan->has_fwd)
+    return set_error("plan was created without the %s tables", inverse ? "inverse" : "forward");
+  if(batch == 0) return NTT_B200_SUCCESS;
+  ntt_b200_plan_t *pl = (ntt_b200_plan_t *)plan; /* pipeline state is internal and lock-protected */
+  pthread_mutex_lock(&pl->pipe_lock);
+  int rc = pipe_prepare(pl);
+  const size_t poly_words = (size_t)pl->N;
+  size_t       done = 0;
+  int          slot = 0;
+  while(!rc && done < batch) {
+    const size_t take  = batch - done < pl->pipe_polys ? batch - done : pl->pipe_polys;
+    const size_t bytes = take * poly_words * 8;
+    void *       st    = pl->pipe_stream[slot];
+    uint64_t *   d     = pl->pipe_buf[slot];
+    /* the slot's previous D2H must have drained before its buffer is overwritten */
+    if(ntt_cuda_sync(pl->device, st)) rc = cuda_error("pipeline sync");
+    if(!rc && ntt_cuda_h2d(pl->device, d, h_a + done * poly_words, bytes, st)) rc = cuda_error("H2D copy");
+    if(!rc && (inverse ? ntt_cuda_inverse(pl->device, &pl->params, d, take, st)
+                       : ntt_cuda_forward(pl->device, &pl->params, d, take, st)))
+      rc = cuda_error("transform");
+    if(!rc && ntt_cuda_d2h(pl->device, h_a + done * poly_words, d, bytes, st)) rc = cuda_error("D2H copy");
+    done += take;
+    slot = (slot + 1) % HOST_PIPE_DEPTH;
+  }
+  for(int i = 0; i < HOST_PIPE_DEPTH; i++) {
+    if(pl->pipe_stream[i] && ntt_cuda_sync(pl->device, pl->pipe_stream[i]) && !rc) rc = cuda_error("pipeline sync");
+  }
+  pthread_mutex_unlock(&pl->pipe_lock);
+  return rc;
+}
+
+int ntt_b200_fwd_batch_host(const ntt_b200_plan_t *plan, uint64_t *h_a, size_t batch)
+{
+  return host_apply(plan, h_a, batch, 0);
+}
+int ntt_b200_inv_batch_host(const ntt_b200_plan_t *plan, uint64_t *h_a, size_t batch)
+{
+  return host_apply(plan, h_a, batch, 1);
+}
+
+int ntt_b200_host_alloc(void **ptr, size_t bytes)
+{
+  if(!ptr) return set_error("NULL argument%s", NULL);
+  if(ntt_cuda_host_alloc(ptr, bytes)) return cuda_error("pinned alloc");
+  return NTT_B200_SUCCESS;
+}
+int ntt_b200_host_free(void *ptr)
+{
+  if(ptr && ntt_cuda_host_free(ptr)) return cuda_error("pinned free");
+  return NTT_B200_SUCCESS;
+}
+int ntt_b200_device_alloc(int device, void **d_ptr, size_t bytes)
+{
+  if(!d_ptr) return set_error("NULL argument%s", NULL);
+  if(ntt_cuda_malloc(device, d_ptr, bytes)) return cuda_error("device alloc");
+  return NTT_B200_SUCCESS;
+}
+int ntt_b200_device_free(int device, void *d_ptr)
+{
+  if(d_ptr && ntt_cuda_free(device, d_ptr)) return cuda_error("device free");
+  return NTT_B200_SUCCESS;
+}
+int ntt_b200_memcpy_h2d(int device, void *d_dst, const void *h_src, size_t bytes)
+{
+  if(ntt_cuda_h2d(device, d_dst, h_src, bytes, NULL) || ntt_cuda_sync(device, NULL)) return cuda_error("H2D copy");
+  return NTT_B200_SUCCESS;
+}
+int ntt_b200_memcpy_d2h(int device, void *h_dst, const void *d_src, size_t bytes)
+{
+  if(ntt_cuda_d2h(device, h_dst, d_src, bytes, NULL) || ntt_cuda_sync(device, NULL)) return cuda_error("D2H copy");
+  return NTT_B200_SUCCESS;
+}
+int ntt_b200_device_sync(int device)
+{
+  if(ntt_cuda_sync(device, NULL)) return cuda_error("device sync");
+  return NTT_B200_SUCCESS;
+}
+
+/* ---- host-side table builders (pre_compute.h:16-83 replacements) ------------------------------------- */
+
+uint64_t ntt_b200_bit_rev_idx(uint64_t idx, uint64_t width) { return nttm_bitrev(idx, (unsigned)width); }
+
+int ntt_b200_calc_w(uint64_t *out, uint64_t root, uint64_t N, uint64_t q)
+{
+  if(!out || N < 1 || (N & (N - 1)) != 0 || q < 2) return set_error("bad arguments to calc_w%s", NULL);
+  const unsigned m   = nttm_log2(N);
+  uint64_t       pwr = 1 % q;
+  for(uint64_t i = 0; i < N; i++) {
+    out[nttm_bitrev(i, m)] = pwr;
+    pwr                    = nttm_mulmod(pwr, root % q, q);
+  }
+  return NTT_B200_SUCCESS;
+}
+
+int ntt_b200_calc_w_con(uint64_t *out, const uint64_t *w, uint64_t N, uint64_t q, uint64_t word_size)
+{
+  if(!out || !w || q < 2 || word_size > 64) return set_error("bad arguments to calc_w_con%s", NULL);
+  for(uint64_t i = 0; i < N; i++) out[i] = nttm_shoup(w[i], q, (unsigned)word_size);
+  return NTT_B200_SUCCESS;
+}
+
+uint64_t ntt_b200_calc_ninv_con(uint64_t n_inv, uint64_t q, uint64_t word_size)
+{
+  return nttm_shoup(n_inv, q, (unsigned)word_size);
+}
+
+uint64_t ntt_b200_pow_mod(uint64_t a, uint64_t e, uint64_t q) { return nttm_powmod(a, e, q); }
+uint64_t ntt_b200_inv_mod(uint64_t a, uint64_t q) { return nttm_invmod_prime(a, q); }
+int      ntt_b200_is_prime(uint64_t n) { return nttm_is_prime(n); }
+uint64_t ntt_b200_min_primitive_root(uint64_t N, uint64_t q) { return nttm_min_primitive_root_2n(N, q); }

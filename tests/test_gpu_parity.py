@@ -1,0 +1,332 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI (include/ntt_b200.h), against the oracle.
+
+They mirror tests/test_correctness.c of the reference (every case: forward == fwd_ntt_ref_harvey after full
+reduction, inverse(forward(a)) == a, the _dbl entry point equals two single transforms) and add what
+SURVEY.md section 4 asks for: full-range and lazy-range inputs, edge vectors, batches of distinct
+polynomials, device-generated tables, and size-independent properties at the benchmark sizes.
+Bit-exact comparison everywhere (integer arithmetic).
+"""
+import numpy as np
+import pytest
+
+from conftest import CaseTables, edge_inputs
+
+pytestmark = pytest.mark.gpu
+
+ALL_CASES = list(range(19))
+
+
+def _torch():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+def to_dev(a):
+    torch = _torch()
+    return torch.from_numpy(np.ascontiguousarray(a).view(np.int64)).cuda()
+
+
+def to_host(t):
+    return t.cpu().numpy().view(np.uint64)
+
+
+# ---- the 19 fixture cases through the reference-shaped entry points ------------------------------------
+
+@pytest.mark.parametrize("idx", ALL_CASES)
+def test_fixture_case_dropin(ntt, oracle, golden_cases, case_tables, idx):
+    g, t = golden_cases[idx], case_tables(idx)
+    a = oracle.uniform(t.N, t.q, 0x5EED0000 + idx)
+    assert "%016x" % oracle.fnv(a) == g["in_fnv"]
+
+    x = a.copy()
+    ntt.fwd_ntt_ref_harvey(x, t.N, t.q, t.w, t.w_con)
+    assert np.array_equal(x, oracle.fwd(a, t.q, t.w, t.w_con)), "forward differs from oracle"
+    assert "%016x" % oracle.fnv(x) == g["fwd_fnv"], "forward differs from the reference's golden hash"
+
+    # lazy entry point: contract is [0,4q) and equality after full reduction (test_correctness.c:267-269)
+    y = a.copy()
+    ntt.fwd_ntt_ref_harvey_lazy(y, t.N, t.q, t.w, t.w_con)
+    assert (y < 4 * t.q).all()
+    assert np.array_equal(y % np.uint64(t.q), x)
+
+    ntt.inv_ntt_ref_harvey(x, t.N, t.q, t.n_inv, t.n_inv_con, 64, t.w_inv, t.w_inv_con)
+    assert np.array_equal(x, a), "inverse(forward(a)) != a"
+
+
+@pytest.mark.parametrize("idx", ALL_CASES)
+def test_fixture_case_lazy_range_inputs(ntt, oracle, golden_cases, case_tables, idx):
+    """Inputs at the edge of the reference's input contracts: [0,4q) forward, [0,2q) inverse."""
+    g, t = golden_cases[idx], case_tables(idx)
+    a4 = oracle.uniform(t.N, 4 * t.q, 0x4A2F0000 + idx)
+    x = a4.copy()
+    ntt.fwd_ntt_ref_harvey(x, t.N, t.q, t.w, t.w_con)
+    assert "%016x" % oracle.fnv(x) == g["fwd4q_fnv"]
+    assert np.array_equal(x, oracle.fwd(a4, t.q, t.w, t.w_con))
+
+    a2 = oracle.uniform(t.N, 2 * t.q, 0x2A2F0000 + idx)
+    y = a2.copy()
+    ntt.inv_ntt_ref_harvey(y, t.N, t.q, t.n_inv, t.n_inv_con, 64, t.w_inv, t.w_inv_con)
+    assert "%016x" % oracle.fnv(y) == g["inv2q_fnv"]
+    assert np.array_equal(y, oracle.inv(a2, t.q, t.n_inv, t.w_inv, t.w_inv_con))
+
+    # worst case for the lazy accumulators: every coefficient at the top of the range
+    top = np.full(t.N, 4 * t.q - 1, dtype=np.uint64)
+    z = top.copy()
+    ntt.fwd_ntt_ref_harvey(z, t.N, t.q, t.w, t.w_con)
+    assert np.array_equal(z, oracle.fwd(top, t.q, t.w, t.w_con))
+    top2 = np.full(t.N, 2 * t.q - 1, dtype=np.uint64)
+    z = top2.copy()
+    ntt.inv_ntt_ref_harvey(z, t.N, t.q, t.n_inv, t.n_inv_con, 64, t.w_inv, t.w_inv_con)
+    assert np.array_equal(z, oracle.inv(top2, t.q, t.n_inv, t.w_inv, t.w_inv_con))
+
+
+@pytest.mark.parametrize("idx", [0, 5, 9, 12, 13, 15, 18])
+def test_fixture_case_edges_and_dbl(ntt, oracle, golden_cases, case_tables, idx):
+    g, t = golden_cases[idx], case_tables(idx)
+    for name, v in edge_inputs(t.N, t.q).items():
+        x = v.copy()
+        ntt.fwd_ntt_ref_harvey(x, t.N, t.q, t.w, t.w_con)
+        assert "%016x" % oracle.fnv(x) == g["edges"][name]["fwd"], name
+        y = v.copy()
+        ntt.inv_ntt_ref_harvey(y, t.N, t.q, t.n_inv, t.n_inv_con, 64, t.w_inv, t.w_inv_con)
+        assert "%016x" % oracle.fnv(y) == g["edges"][name]["inv"], name
+    # double-input entry point: both lanes equal the single-input result (test_correctness.c:40-59)
+    a = oracle.uniform(t.N, t.q, 77 + idx)
+    a1, a2 = a.copy(), a.copy()
+    ntt.fwd_ntt_ref_harvey_dbl(a1, a2, t.N, t.q, t.w, t.w_con)
+    want = oracle.fwd(a, t.q, t.w, t.w_con)
+    assert np.array_equal(a1, want) and np.array_equal(a2, want)
+
+
+def test_case0_full_vectors(ntt, golden_case0):
+    g = golden_case0
+    N, q = 1 << g["m"], g["q"]
+    w, wc = np.array(g["w"], dtype=np.uint64), np.array(g["w_con"], dtype=np.uint64)
+    a = np.array(g["a"], dtype=np.uint64)
+    ntt.fwd_ntt_ref_harvey(a, N, q, w, wc)
+    assert a.tolist() == g["fwd"]
+
+
+# ---- plan / batch API on device-resident data -------------------------------------------------------
+
+@pytest.mark.parametrize("idx", [0, 3, 6, 9, 12, 13, 14, 15, 16, 17, 18])
+def test_batch_api_distinct_polynomials(ntt, oracle, case_tables, idx):
+    t = case_tables(idx)
+    batch = 5 if t.m <= 14 else 3
+    plan = ntt.Plan.from_tables(t.N, t.q, t.w, t.w_con, t.w_inv, t.w_inv_con, t.n_inv, t.n_inv_con)
+    a = oracle.uniform(batch * t.N, t.q, 1000 + idx).reshape(batch, t.N)
+    d = to_dev(a)
+    plan.fwd(d, batch)
+    f = to_host(d)
+    assert np.array_equal(f, oracle.fwd(a, t.q, t.w, t.w_con))
+    plan.inv(d, batch)
+    assert np.array_equal(to_host(d), a)
+    plan.close()
+
+
+@pytest.mark.parametrize("idx", [0, 4, 9, 13, 16, 18])
+def test_device_generated_tables_match_reference_tables(ntt, oracle, golden_cases, case_tables, idx):
+    """north star item 4: tables generated on the device equal calc_w / calc_w_con output bit for bit."""
+    g, t = golden_cases[idx], case_tables(idx)
+    plan = ntt.Plan.from_psi(t.N, t.q, t.psi)
+    tb = plan.export_tables()
+    assert "%016x" % oracle.fnv(tb["w"]) == g["w_fnv"]
+    assert "%016x" % oracle.fnv(tb["w_con"]) == g["w_con_fnv"]
+    assert "%016x" % oracle.fnv(tb["w_inv"]) == g["w_inv_fnv"]
+    assert "%016x" % oracle.fnv(tb["w_inv_con"]) == g["w_inv_con_fnv"]
+    assert tb["n_inv"] == g["n_inv"] and tb["n_inv_con"] == g["n_inv_con"]
+    a = oracle.uniform(t.N, t.q, 0x5EED0000 + idx)
+    d = to_dev(a)
+    plan.fwd(d, 1)
+    assert "%016x" % oracle.fnv(to_host(d)) == g["fwd_fnv"]
+    plan.close()
+
+
+def test_exact_path_large_modulus(ntt, oracle):
+    """q above the lazy fast path's limit (2^56) takes the general Harvey kernel (valid to 2^62)."""
+    for bits, m in ((60, 10), (61, 13), (58, 15)):
+        N = 1 << m
+        q = (1 << bits) - (1 << bits) % (2 * N) + 1
+        while not oracle.is_prime(q):
+            q -= 2 * N
+        psi = oracle.min_root(N, q) if m <= 10 else None
+        if psi is None:
+            # any primitive 2N-th root will do for parity
+            x = 2
+            while True:
+                c = oracle.powmod(x, (q - 1) // (2 * N), q)
+                if oracle.powmod(c, N, q) == q - 1:
+                    psi = c
+                    break
+                x += 1
+        t = CaseTables(oracle, m, q, psi, oracle.invmod(psi, q), oracle.invmod(N, q))
+        plan = ntt.Plan.from_tables(t.N, t.q, t.w, t.w_con, t.w_inv, t.w_inv_con, t.n_inv, t.n_inv_con)
+        assert not plan.is_lazy
+        a = oracle.uniform(2 * N, 4 * q, bits).reshape(2, N)
+        d = to_dev(a)
+        plan.fwd(d, 2)
+        f = to_host(d)
+        assert np.array_equal(f, oracle.fwd(a, q, t.w, t.w_con))
+        plan.inv(d, 2)
+        assert np.array_equal(to_host(d), a % np.uint64(q))
+        plan.close()
+
+
+def test_synthetic_configs_golden(ntt, oracle, golden_synth):
+    """The throughput parameter sets (49-bit q; N = 2^13, 2^14, 2^16) against reference-generated hashes."""
+    for s in golden_synth:
+        N, q = 1 << s["m"], s["q"]
+        plan = ntt.Plan.from_psi(N, q, s["psi"])
+        a = oracle.uniform(s["batch"] * N, q, s["seed"]).reshape(s["batch"], N)
+        assert "%016x" % oracle.fnv(a) == s["in_fnv"]
+        d = to_dev(a)
+        plan.fwd(d, s["batch"])
+        assert "%016x" % oracle.fnv(to_host(d)) == s["fwd_fnv"]
+        plan.inv(d, s["batch"])
+        assert np.array_equal(to_host(d), a)
+        plan.close()
+
+
+# ---- size-independent properties at the benchmark sizes ------------------------------------------------
+
+def _spot_check(plan_tables, oracle, a, f, rows):
+    t = plan_tables
+    for r in rows:
+        assert np.array_equal(f[r], oracle.fwd(a[r], t.q, t.w, t.w_con)), "row %d" % r
+
+
+def test_headline_config_roundtrip_and_linearity(ntt, oracle, golden_synth):
+    """BASELINE config 2: N=2^14, 49-bit q, batch 4096 -- round trip, linearity, spot rows vs oracle."""
+    torch = _torch()
+    s = [x for x in golden_synth if x["m"] == 14][0]
+    N, q, batch = 1 << 14, s["q"], 4096
+    t = CaseTables(oracle, 14, q, s["psi"], s["psi_inv"], s["n_inv"])
+    plan = ntt.Plan.from_psi(N, q, s["psi"])
+    a = oracle.uniform(batch * N, q, 1).reshape(batch, N)
+    b = oracle.uniform(batch * N, q, 11).reshape(batch, N)
+    da, db = to_dev(a), to_dev(b)
+    dsum = to_dev((a + b) % np.uint64(q))
+    plan.fwd(da, batch)
+    plan.fwd(db, batch)
+    plan.fwd(dsum, batch)
+    fa, fb, fs = to_host(da), to_host(db), to_host(dsum)
+    assert (fa < q).all() and (fb < q).all()
+    assert np.array_equal((fa + fb) % np.uint64(q), fs), "NTT(a+b) != NTT(a)+NTT(b)"
+    _spot_check(t, oracle, a, fa, [0, 1, 777, 2048, 4095])
+    plan.inv(da, batch)
+    assert np.array_equal(to_host(da), a), "round trip failed at full batch"
+    torch.cuda.synchronize()
+    plan.close()
+
+
+def test_rns_limbs(ntt, oracle):
+    """BASELINE config 3 shape (scaled down): N=2^16, several ~50-bit limbs, each with its own q."""
+    N, m, limbs, per = 1 << 16, 16, 3, 2
+    qs, q = [], (1 << 50) + 1
+    q -= (q - 1) % (2 * N)
+    while len(qs) < limbs:
+        q -= 2 * N
+        if oracle.is_prime(q):
+            qs.append(q)
+    plans, tabs = [], []
+    for q in qs:
+        psi = oracle.min_root(N, q)
+        plans.append(ntt.Plan.from_psi(N, q, psi))
+        tabs.append(CaseTables(oracle, m, q, psi, oracle.invmod(psi, q), oracle.invmod(N, q)))
+    a = np.stack([oracle.uniform(per * N, q, 5 + i).reshape(per, N) for i, q in enumerate(qs)])
+    d = to_dev(a)
+    ntt.fwd_rns(plans, d, per)
+    f = to_host(d)
+    for i, t in enumerate(tabs):
+        assert np.array_equal(f[i], oracle.fwd(a[i], t.q, t.w, t.w_con))
+    ntt.inv_rns(plans, d, per)
+    assert np.array_equal(to_host(d), a)
+    for p in plans:
+        p.close()
+
+
+def test_negacyclic_polymul(ntt, oracle, golden_synth):
+    """BASELINE config 4 shape: c = INTT(NTT(a) o NTT(b)); checked against schoolbook and oracle NTTs."""
+    # small ring: exact schoolbook product
+    N, q = 256, 7681
+    plan = ntt.Plan.from_psi(N, q, 62)
+    a, b = oracle.uniform(N, q, 21), oracle.uniform(N, q, 22)
+    da, db = to_dev(a), to_dev(b)
+    plan.negacyclic_mul(da, da, db, 1)
+    assert np.array_equal(to_host(da), oracle.negacyclic_mul(a, b, q))
+    plan.close()
+    # N = 2^13, 49-bit q: against the oracle pipeline fwd, fwd, pointwise, inv
+    s = [x for x in golden_synth if x["m"] == 13][0]
+    N, q, batch = 1 << 13, s["q"], 8
+    t = CaseTables(oracle, 13, q, s["psi"], s["psi_inv"], s["n_inv"])
+    plan = ntt.Plan.from_psi(N, q, s["psi"])
+    a = oracle.uniform(batch * N, q, 31).reshape(batch, N)
+    b = oracle.uniform(batch * N, q, 32).reshape(batch, N)
+    da, db = to_dev(a), to_dev(b)
+    dc = to_dev(np.zeros_like(a))
+    plan.negacyclic_mul(dc, da, db, batch)
+    fa, fb = oracle.fwd(a, q, t.w, t.w_con), oracle.fwd(b, q, t.w, t.w_con)
+    prod = oracle.pointwise_mul(fa, fb, q).reshape(batch, N)
+    want = oracle.inv(prod, q, t.n_inv, t.w_inv, t.w_inv_con)
+    assert np.array_equal(to_host(dc), want)
+    plan.close()
+
+
+def test_host_batch_api_pinned_and_pageable(ntt, oracle, golden_synth):
+    torch = _torch()
+    s = [x for x in golden_synth if x["m"] == 14][0]
+    N, q, batch = 1 << 14, s["q"], 600  # > one pipeline chunk (32 MiB = 256 polynomials)
+    t = CaseTables(oracle, 14, q, s["psi"], s["psi_inv"], s["n_inv"])
+    plan = ntt.Plan.from_psi(N, q, s["psi"])
+    a = oracle.uniform(batch * N, q, 41).reshape(batch, N)
+    pageable = a.copy()
+    plan.fwd_host(pageable, batch)
+    pinned = torch.from_numpy(a.view(np.int64).copy()).pin_memory()
+    plan.fwd_host(pinned, batch)
+    f = pinned.numpy().view(np.uint64)
+    assert np.array_equal(f, pageable)
+    for r in (0, 255, 256, 599):
+        assert np.array_equal(f[r], oracle.fwd(a[r], q, t.w, t.w_con))
+    plan.inv_host(pinned, batch)
+    assert np.array_equal(pinned.numpy().view(np.uint64), a)
+    plan.close()
+
+
+def test_large_n_two_pass_split(ntt, oracle):
+    """N = 2^20 (strided passes + chunk kernel): one polynomial against the oracle."""
+    m, q = 20, 0x1FFFFFC800001
+    N = 1 << m
+    x = 2
+    while True:
+        psi = oracle.powmod(x, (q - 1) // (2 * N), q)
+        if oracle.powmod(psi, N, q) == q - 1:
+            break
+        x += 1
+    t = CaseTables(oracle, m, q, psi, oracle.invmod(psi, q), oracle.invmod(N, q))
+    plan = ntt.Plan.from_psi(N, q, psi)
+    a = oracle.uniform(N, q, 4)
+    d = to_dev(a)
+    plan.fwd(d, 1)
+    assert np.array_equal(to_host(d), oracle.fwd(a, q, t.w, t.w_con))
+    plan.inv(d, 1)
+    assert np.array_equal(to_host(d), a)
+    plan.close()
+
+
+def test_error_behaviour(ntt, oracle, case_tables):
+    t = case_tables(0)
+    with pytest.raises(ntt.NttError):
+        ntt.Plan.from_psi(t.N, t.q, 3)  # not a primitive 2N-th root
+    with pytest.raises(ntt.NttError):
+        ntt.Plan.from_psi(t.N + 1, t.q, t.psi)  # N not a power of two
+    bad = t.w_con.copy()
+    bad[5] ^= 1
+    with pytest.raises(ntt.NttError):
+        ntt.Plan.from_tables(t.N, t.q, t.w, bad)  # companion table inconsistent with q
+    fwd_only = ntt.Plan.from_tables(t.N, t.q, t.w, t.w_con)
+    d = to_dev(np.zeros(t.N, dtype=np.uint64))
+    with pytest.raises(ntt.NttError):
+        fwd_only.inv(d, 1)
+    fwd_only.fwd(d, 0)  # empty batch is a no-op
+    fwd_only.close()
