@@ -18,7 +18,7 @@ extern "C" {
 #define NTT_MAX_STAGES 24
 
 /* One modular multiplier in the device's "split" form (lazy path), see csrc/ntt_device.cuh:
- *   w  : the multiplier, u = w * 2^32 mod q, wq = floor(w * 2^31 / q), uq = floor(u * 2^31 / q)
+ *   w  : the multiplier, u = w * 2^32 mod q, wq = floor(w * 2^30 / q), uq = floor(u * 2^30 / q)
  * or, on the exact (Harvey) path: w and c = floor(w * 2^64 / q) in (u0,u1). */
 typedef struct ntt_cuda_mulc {
   uint32_t w0, w1, u0, u1;
@@ -30,6 +30,7 @@ typedef struct ntt_cuda_params {
   uint64_t q;
   uint64_t neg2q;   /* 2^64 - 2q (lazy path) */
   uint64_t negq;    /* 2^64 - q */
+  uint64_t c10q;    /* 10q: bound of a lazy product, added to keep differences non-negative */
   uint32_t logn;
   uint32_t lazy;    /* 1: lazy split-multiplier path, 0: exact Harvey path */
   uint32_t red_shift; /* final reduction: vt = v >> red_shift, Q = hi32(vt * red_mu) */
@@ -39,6 +40,12 @@ typedef struct ntt_cuda_params {
   const void *fwd_qq;
   const void *inv_wu;
   const void *inv_qq;
+  /* the last four stages again, laid out [t][group] (t = 2^u-1+sub, group = 16-coefficient run, N/16 per
+   * polynomial) so that the 32 threads of a warp read 32 consecutive entries (ring kernel, pass C) */
+  const void *fwd_ct_wu;
+  const void *fwd_ct_qq;
+  const void *inv_ct_wu;
+  const void *inv_ct_qq;
   /* inverse last stage: N^-1 and N^-1 * w_inv[1] as multipliers */
   ntt_cuda_mulc_t ninv;
   ntt_cuda_mulc_t ninv_w1;
@@ -68,6 +75,9 @@ int ntt_cuda_plan_inverse_bounds(ntt_cuda_params_t *p);
  * on the device (d_w).  d_con_out (may be NULL) receives floor(w*2^64/q) for validation/export. */
 int ntt_cuda_build_tables(int device, const ntt_cuda_params_t *p, const uint64_t *d_w, void *d_wu, void *d_qq,
                           uint64_t *d_con_out, uint64_t N, void *stream);
+/* Re-lay the last four stages of (wu, qq) into the [15][N/16] pass-C tables (N >= 16). */
+int ntt_cuda_build_ctables(int device, const ntt_cuda_params_t *p, const void *d_wu, const void *d_qq, void *d_ct_wu,
+                           void *d_ct_qq, void *stream);
 /* Generate the reference-format table d_w[bitrev(i)] = root^i mod q on the device. */
 int ntt_cuda_gen_root_table(int device, uint64_t *d_w, uint64_t root, uint64_t N, uint64_t q, void *stream);
 

@@ -8,14 +8,14 @@
  * Two multiplier forms implement the reference's Shoup product fast_mul_mod_q2
  * (include/internal/fast_mul_operators.h:49-54):
  *
- *  (1) LAZY SPLIT form (default; any q with (4+6*log2N)*q < 2^64, i.e. every q below ~2^56):
- *      a multiplier w is stored as  w, u = w*2^32 mod q, wq = floor(w*2^31/q), uq = floor(u*2^31/q).
+ *  (1) LAZY SPLIT form (default; any q with (4+10*log2N)*q < 2^64, i.e. every q below 2^56):
+ *      a multiplier w is stored as  w, u = w*2^32 mod q, wq = floor(w*2^30/q), uq = floor(u*2^30/q).
  *      For y = y1*2^32 + y0:   w*y == w*y0 + u*y1 =: V (mod q), V < q*2^33.
- *      S = floor((wq*y0 + uq*y1) / 2^32) satisfies V/(2q) - 3 < S <= V/(2q), so
- *      r = V - S*2q lies in [0, 6q) and r == w*y (mod q).  Cost: 8 IMAD (2 for S, 6 for r mod 2^64),
- *      against 10 IMAD + carry adds for the textbook 64-bit Shoup product.
- *      Because r < 6q regardless of y, butterflies need NO conditional subtraction: values simply
- *      grow by 6q per forward stage and are brought back once at the end (reduce_full).
+ *      S = floor((wq*y0 + uq*y1) / 2^31) satisfies V/(2q) - 5 < S <= V/(2q), so
+ *      r = V - S*2q lies in [0, 10q) and r == w*y (mod q).  Cost: 8 IMAD (2 for S, 6 for r mod 2^64)
+ *      + 1 funnel shift, against 10 IMAD + carry adds for the textbook 64-bit Shoup product.
+ *      Because r < 10q regardless of y, butterflies need NO conditional subtraction: values simply
+ *      grow by 10q per forward stage and are brought back once at the end (reduce_full).
  *
  *  (2) EXACT form (q up to 2^62): w and c = floor(w*2^64/q); r = w*y - hi64(c*y)*q in [0,2q), the
  *      reference's arithmetic bit for bit, with Harvey's per-stage conditional subtractions
@@ -62,12 +62,16 @@ __device__ __forceinline__ uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c)
   return r;
 }
 
-/* r == m*y (mod q), r in [0,6q).  n2q = 2^64 - 2q.  8 IMAD. */
-__device__ __forceinline__ uint64_t mul_lazy(uint64_t y, const Mulc &m, uint64_t n2q)
+/* r == m*y (mod q), r in [0,10q).  n2q = 2^64 - 2q.  8 full-rate IMAD + 1 SHF.
+ * A = wq*y0 + uq*y1 < 2^63 (30-bit companions); S = floor(A/2^31) obeys V/(2q) - 5 < S <= V/(2q).
+ * Shifting by 31 rather than taking the high word keeps both halves of A live, so ptxas cannot fuse the
+ * second IMAD.WIDE into a half-rate IMAD.HI. */
+__device__ __forceinline__ uint64_t mul_lazy_acc(uint64_t y, const Mulc &m, uint64_t n2q, uint64_t acc)
 {
   const uint32_t y0 = lo32(y), y1 = hi32(y);
-  const uint32_t S  = hi32(mad_wide(m.uq, y1, mul_wide(m.wq, y0)));
-  uint64_t       r  = mul_wide(m.w0, y0);
+  const uint64_t a  = mad_wide(m.uq, y1, mul_wide(m.wq, y0));
+  const uint32_t S  = __funnelshift_r(lo32(a), hi32(a), 31);
+  uint64_t       r  = mad_wide(m.w0, y0, acc);
   r                 = mad_wide(m.u0, y1, r);
   r                 = mad_wide(S, lo32(n2q), r);
   uint32_t rh       = hi32(r);
@@ -75,6 +79,10 @@ __device__ __forceinline__ uint64_t mul_lazy(uint64_t y, const Mulc &m, uint64_t
   rh                = mad_lo(m.u1, y1, rh);
   rh                = mad_lo(S, hi32(n2q), rh);
   return pack64(lo32(r), rh);
+}
+__device__ __forceinline__ uint64_t mul_lazy(uint64_t y, const Mulc &m, uint64_t n2q)
+{
+  return mul_lazy_acc(y, m, n2q, 0);
 }
 
 /* hi64(a*b) from four IMAD.WIDE (exact) */
@@ -135,10 +143,11 @@ __device__ __forceinline__ Mulc mulc_from(const ntt_cuda_mulc_t &m)
 /* ---- butterflies -------------------------------------------------------------------------------- */
 
 /* forward (Cooley-Tukey) butterfly, harvey_fwd_butterfly fast_mul_operators.h:72-81.
- * lazy: X' = X + T, Y' = X - T + 6q with T in [0,6q): both outputs < X + 6q. */
+ * lazy: X' = X + T, Y' = X - T + 10q with T in [0,10q): both outputs < X + 10q.  X' comes straight out of
+ * the multiply-accumulate chain (X is its addend) and Y' = 2X + 10q - X'. */
 template <bool EXACT>
 __device__ __forceinline__ void bfly_fwd(uint64_t &x, uint64_t &y, const Mulc &m, const ntt_cuda_params_t &p,
-                                         uint64_t c6q)
+                                         uint64_t c10q)
 {
   if(EXACT) {
     const uint64_t q2 = p.q << 1;
@@ -147,14 +156,14 @@ __device__ __forceinline__ void bfly_fwd(uint64_t &x, uint64_t &y, const Mulc &m
     x                 = x1 + t;
     y                 = x1 - t + q2;
   } else {
-    const uint64_t t = mul_lazy(y, m, p.neg2q);
-    y                = x - t + c6q;
-    x                = x + t;
+    const uint64_t xs = mul_lazy_acc(y, m, p.neg2q, x);
+    y                 = (x + x + c10q) - xs;
+    x                 = xs;
   }
 }
 
 /* inverse (Gentleman-Sande) butterfly, harvey_bkw_butterfly fast_mul_operators.h:83-92.
- * lazy: X' = X + Y (< 2B q), Y' = m * (X - Y + B q) in [0,6q), where cb = B*q bounds the inputs. */
+ * lazy: X' = X + Y (< 2B q), Y' = m * (X - Y + B q) in [0,10q), where cb = B*q bounds the inputs. */
 template <bool EXACT>
 __device__ __forceinline__ void bfly_inv(uint64_t &x, uint64_t &y, const Mulc &m, const ntt_cuda_params_t &p,
                                          uint64_t cb)
@@ -173,7 +182,7 @@ __device__ __forceinline__ void bfly_inv(uint64_t &x, uint64_t &y, const Mulc &m
 }
 
 /* last inverse stage with N^-1 folded in, harvey_bkw_butterfly_final fast_mul_operators.h:94-106.
- * Outputs are left lazy (< 6q, or < 2q exact); the caller applies the final reduction. */
+ * Outputs are left lazy (< 10q, or < 2q exact); the caller applies the final reduction. */
 template <bool EXACT>
 __device__ __forceinline__ void bfly_inv_final(uint64_t &x, uint64_t &y, const Mulc &ninv, const Mulc &ninv_w,
                                                const ntt_cuda_params_t &p, uint64_t cb)

@@ -23,8 +23,13 @@
 #include <cstdio>
 #include <cstring>
 
+#include <cuda.h>
+
+#include <cstdlib>
+
 #include "ntt_cuda.h"
 #include "ntt_device.cuh"
+#include "ntt_ring.cuh"
 
 using namespace nttb200;
 
@@ -97,7 +102,7 @@ __device__ __forceinline__ void radix_network(uint64_t (&x)[1 << R], const ntt_c
                                               uint32_t blk0)
 {
   constexpr int n   = 1 << R;
-  const uint64_t c6 = 6 * p.q;
+  const uint64_t c10 = p.c10q;
   if(FWD) {
 #pragma unroll
     for(int u = 0; u < R; u++) {
@@ -106,7 +111,7 @@ __device__ __forceinline__ void radix_network(uint64_t (&x)[1 << R], const ntt_c
       for(int sub = 0; sub < (1 << u); sub++) {
         const Mulc m = tw<EXACT>(p, true, s0 + u, (blk0 << u) + sub);
 #pragma unroll
-        for(int k = 0; k < d; k++) bfly_fwd<EXACT>(x[sub * 2 * d + k], x[sub * 2 * d + k + d], m, p, c6);
+        for(int k = 0; k < d; k++) bfly_fwd<EXACT>(x[sub * 2 * d + k], x[sub * 2 * d + k + d], m, p, c10);
       }
     }
   } else {
@@ -351,7 +356,7 @@ __global__ void k_build_tables(const uint64_t *__restrict__ d_w, uint4 *__restri
     if(lazy) {
       const uint64_t u = (uint64_t)((((u128)w) << 32) % q);
       wu[i]            = make_uint4((uint32_t)w, (uint32_t)(w >> 32), (uint32_t)u, (uint32_t)(u >> 32));
-      qq[i]            = make_uint2((uint32_t)((((u128)w) << 31) / q), (uint32_t)((((u128)u) << 31) / q));
+      qq[i]            = make_uint2((uint32_t)((((u128)w) << 30) / q), (uint32_t)((((u128)u) << 30) / q));
     } else {
       wu[i] = make_uint4((uint32_t)w, (uint32_t)(w >> 32), (uint32_t)c, (uint32_t)(c >> 32));
       qq[i] = make_uint2(0u, 0u);
@@ -501,6 +506,122 @@ extern "C" int ntt_cuda_build_tables(int device, const ntt_cuda_params_t *p, con
   return 0;
 }
 
+/* ---- pass-C tables ---------------------------------------------------------------------------------- */
+
+/* ct[t*G + g] = entry 2^(logn-4+u) + g*2^u + sub of the stage tables, t = 2^u-1+sub, G = N/16 */
+__global__ void k_build_ctables(const uint4 *__restrict__ wu, const uint2 *__restrict__ qq, uint4 *__restrict__ ct_wu,
+                                uint2 *__restrict__ ct_qq, uint32_t logn)
+{
+  const size_t G = (size_t)1 << (logn - 4);
+  for(size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < 15 * G; i += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t t = (uint32_t)(i / G);
+    const size_t   g = i % G;
+    const uint32_t u = 31u - __clz(t + 1u), sub = t + 1u - (1u << u);
+    const size_t   src = ((size_t)1 << (logn - 4 + u)) + (g << u) + sub;
+    ct_wu[i] = wu[src];
+    ct_qq[i] = qq[src];
+  }
+}
+
+extern "C" int ntt_cuda_build_ctables(int device, const ntt_cuda_params_t *p, const void *d_wu, const void *d_qq,
+                                      void *d_ct_wu, void *d_ct_qq, void *stream)
+{
+  DevGuard g(device);
+  if(!g.ok) return fail_msg("cudaSetDevice failed");
+  if(p->logn < 4) return fail_msg("pass-C tables need N >= 16");
+  const size_t total  = (size_t)15 << (p->logn - 4);
+  const int    blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+  k_build_ctables<<<blocks, 256, 0, (cudaStream_t)stream>>>((const uint4 *)d_wu, (const uint2 *)d_qq, (uint4 *)d_ct_wu,
+                                                           (uint2 *)d_ct_qq, p->logn);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+/* ---- ring kernel launch ------------------------------------------------------------------------------ */
+
+typedef CUresult (*tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static tmap_encode_fn tmap_encoder()
+{
+  static tmap_encode_fn fn = nullptr;
+  if(!fn) {
+    void *                          sym = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qr) == cudaSuccess &&
+       qr == cudaDriverEntryPointSuccess)
+      fn = (tmap_encode_fn)sym;
+  }
+  return fn;
+}
+
+/* The coefficient array seen as rows of 128 bytes (32 x u32); one TMA box = 32 rows = one 512-coefficient
+ * block, written to shared memory with the 128-byte swizzle the passes are laid out for. */
+static int make_block_tmap(CUtensorMap *tm, uint64_t *d_a, size_t total_words)
+{
+  tmap_encode_fn enc = tmap_encoder();
+  if(!enc) return fail_msg("cuTensorMapEncodeTiled not available from the driver");
+  const cuuint64_t dims[2]    = {32, (cuuint64_t)(total_words / 16)};
+  const cuuint64_t strides[1] = {128};
+  const cuuint32_t box[2]     = {32, 32};
+  const cuuint32_t estr[2]    = {1, 1};
+  const CUresult   r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, d_a, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if(r != CUDA_SUCCESS) {
+    snprintf(g_err, sizeof(g_err), "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return -1;
+  }
+  return 0;
+}
+
+static bool ring_enabled()
+{
+  static int on = -1;
+  if(on < 0) {
+    const char *e = getenv("NTT_B200_NO_RING");
+    on            = (e && e[0] == '1') ? 0 : 1;
+  }
+  return on == 1;
+}
+
+template <int L, bool FWD>
+static int launch_ring(int device, const ntt_cuda_params_t &p, uint64_t *d_a, size_t n_chunks, cudaStream_t st)
+{
+  using C = RingCfg<L>;
+  auto        kern = k_ring<L, FWD>;
+  static bool ready[64] = {false};
+  if(!ready[device & 63]) {
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    ready[device & 63] = true;
+  }
+  CUtensorMap tm;
+  if(make_block_tmap(&tm, d_a, n_chunks << L)) return -1;
+  size_t grid = (size_t)sm_count(device) * C::CTAS;
+  if(grid > n_chunks) grid = n_chunks;
+  kern<<<(unsigned)grid, C::THREADS, C::SMEM, st>>>(p, tm, n_chunks);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+/* true if the ring kernel handled the chunk stage (lazy path, chunk of 2^12..2^14, pass-C tables present) */
+template <bool FWD>
+static int try_ring(int device, int L, const ntt_cuda_params_t &p, uint64_t *d_a, size_t n_chunks, cudaStream_t st,
+                    bool *done)
+{
+  *done = false;
+  if(!ring_enabled() || !p.lazy || L < 12 || L > 14) return 0;
+  if(!(FWD ? p.fwd_ct_wu : p.inv_ct_wu)) return 0;
+  if(((uintptr_t)d_a & 127) != 0) return 0; /* TMA wants 128-byte aligned rows (cudaMalloc gives 256) */
+  *done = true;
+  switch(L) {
+    case 12: return launch_ring<12, FWD>(device, p, d_a, n_chunks, st);
+    case 13: return launch_ring<13, FWD>(device, p, d_a, n_chunks, st);
+    default: return launch_ring<14, FWD>(device, p, d_a, n_chunks, st);
+  }
+}
+
 /* ---- transform dispatch ---------------------------------------------------------------------------- */
 
 template <int L, bool FWD, bool EXACT>
@@ -626,7 +747,7 @@ extern "C" int ntt_cuda_plan_inverse_bounds(ntt_cuda_params_t *p)
     for(int u = 0; u < rads[k]; u++) {
       const int s = tops[k] - u;
       p->inv_c[s] = (uint64_t)B * p->q;
-      B           = (2 * B > 6.0L) ? 2 * B : 6.0L;
+      B           = (2 * B > 10.0L) ? 2 * B : 10.0L;
     }
   }
   return 0;
@@ -641,6 +762,11 @@ static int forward_impl(int device, const ntt_cuda_params_t &p, uint64_t *d_a, s
     if(dispatch_strided<true, EXACT, false>(device, sp.r[k], p, d_a, s0, batch, st)) return -1;
     s0 += sp.r[k];
   }
+  if(!EXACT) {
+    bool done = false;
+    if(try_ring<true>(device, sp.L, p, d_a, batch << s0, st, &done)) return -1;
+    if(done) return 0;
+  }
   return dispatch_chunk<true, EXACT>(device, sp.L, p, d_a, batch << s0, st);
 }
 
@@ -650,7 +776,9 @@ static int inverse_impl(int device, const ntt_cuda_params_t &p, uint64_t *d_a, s
   const Split sp = make_split((int)p.logn);
   uint32_t    s1 = 0;
   for(int k = 0; k < sp.ns; k++) s1 += sp.r[k];
-  if(dispatch_chunk<false, EXACT>(device, sp.L, p, d_a, batch << s1, st)) return -1;
+  bool done = false;
+  if(!EXACT && try_ring<false>(device, sp.L, p, d_a, batch << s1, st, &done)) return -1;
+  if(!done && dispatch_chunk<false, EXACT>(device, sp.L, p, d_a, batch << s1, st)) return -1;
   uint32_t s0 = s1;
   for(int k = sp.ns - 1; k >= 0; k--) {
     s0 -= sp.r[k];

@@ -1,0 +1,388 @@
+/*
+ * csrc/ntt_ring.cuh -- the headline kernel: persistent CTAs, TMA slot ring, three register-tiled passes.
+ *
+ * A chunk of 2^L coefficients (L = 12, 13, 14; a whole polynomial when N = 2^L) is NB = 2^(L-9) "blocks"
+ * of 512 coefficients (4 KiB).  Shared memory is a ring of SLOTS 4-KiB slots; block g of the CTA's work
+ * sequence lives in slot g mod SLOTS.  Blocks arrive by TMA (cp.async.bulk.tensor, SWIZZLE_128B, one
+ * mbarrier per polynomial-in-flight), results leave by TMA store straight out of the slot, and the slot is
+ * re-armed with the block SLOTS positions further down the sequence.  With SLOTS = 56 at L = 14 the next
+ * polynomial is (almost) completely resident before the current one finishes, so HBM traffic overlaps the
+ * butterflies without any register staging.
+ *
+ * Forward schedule for one chunk (stage numbers local to the chunk; the inverse mirrors it):
+ *   pass A  stages 0 .. RA-1 (RA = L-9): butterflies ACROSS blocks; thread j owns column j of every block
+ *           (element j + 512*k, k < NB): one LDS.64/STS.64 per element, conflict free.
+ *           __syncthreads
+ *   pass B  stages RA .. RA+4: inside a block, 32 elements at stride 16 per thread; the two half-warps of
+ *           warp w own blocks w and w + NB/2.
+ *           __syncwarp   (blocks are warp-private from here on)
+ *   pass C  stages RA+5 .. L-1: 16 contiguous coefficients (one swizzled 128-byte row) per thread, final
+ *           reduction to [0,q), LDS.128/STS.128; then lane 0 issues the TMA store of the finished block.
+ *
+ * Butterflies use the lazy split multiplier of ntt_device.cuh (8 IMAD + 1 SHF + 4 IADD3 per forward
+ * butterfly): no conditional subtraction anywhere before the final reduction.  Twiddles of pass C are per-thread distinct; they come from a table laid out
+ * [t][group] (t = 2^u-1+sub) so that a warp reads 32 consecutive entries (ntt_cuda_params_t::*_ct_*).
+ *
+ * Reference semantics restated: src/ntt_reference.c:11-31 (forward), :33-66 (inverse),
+ * include/ntt_reference.h:19-31 (final reduction).
+ */
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "ntt_cuda.h"
+#include "ntt_device.cuh"
+
+namespace nttb200 {
+
+/* ---- PTX wrappers: mbarrier + TMA -------------------------------------------------------------------- */
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+  asm volatile(
+    "{\n\t"
+    ".reg .pred p;\n\t"
+    "WAIT_%=:\n\t"
+    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+    "@p bra DONE_%=;\n\t"
+    "bra WAIT_%=;\n\t"
+    "DONE_%=:\n\t"
+    "}" ::"r"(bar),
+    "r"(parity)
+    : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init()
+{
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+/* global -> shared tile load (box {32 x u32, 32 rows} = 4 KiB), completion counted on `bar` */
+__device__ __forceinline__ void tma_load_block(uint32_t dst, const CUtensorMap *tm, int row, uint32_t bar)
+{
+  asm volatile(
+    "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
+      "r"(dst),
+    "l"(tm), "r"(0), "r"(row), "r"(bar)
+    : "memory");
+}
+/* shared -> global tile store, tracked by the issuing thread's bulk async-group */
+__device__ __forceinline__ void tma_store_block(const CUtensorMap *tm, int row, uint32_t src)
+{
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tm), "r"(0),
+               "r"(row), "r"(src)
+               : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+/* all of this thread's store groups have finished READING shared memory (slots may be overwritten) */
+__device__ __forceinline__ void tma_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+/* ... and have finished writing global memory */
+__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *tm)
+{
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
+}
+
+/* ---- geometry ---------------------------------------------------------------------------------------------- */
+
+template <int L>
+struct RingCfg {
+  static_assert(L >= 12 && L <= 14, "ring kernel covers chunks of 2^12 .. 2^14");
+  static constexpr int RA        = L - 9;                 /* stages of pass A */
+  static constexpr int NB        = 1 << RA;               /* 512-element blocks per chunk */
+  static constexpr int WARPS     = NB / 2 < 1 ? 1 : NB / 2;
+  static constexpr int THREADS   = WARPS * 32;
+  static constexpr int CTAS      = 512 / THREADS < 8 ? 512 / THREADS : 8; /* resident CTAs per SM */
+  /* ring depth: everything that fits next to the 1 KiB per-CTA system reservation (228 KiB per SM) */
+  static constexpr int SLOTS     = CTAS == 1 ? 56 : (CTAS == 2 ? 27 : 13);
+  static constexpr int NBAR      = 4;                     /* polynomials in flight (mbarrier ring) */
+  static constexpr int SMEM      = SLOTS * 4096 + 1024 /* alignment slack */ + 64 /* barriers */;
+  static constexpr int GROUPS_A  = 512;                   /* columns */
+};
+
+/* byte offset of coefficient o (0..511) inside a 4-KiB slot under TMA SWIZZLE_128B (rows of 128 bytes) */
+__device__ __forceinline__ uint32_t slot_off(uint32_t o)
+{
+  const uint32_t row = o >> 4, c16 = (o >> 1) & 7u;
+  return (row << 7) + (((c16 ^ (row & 7u)) << 4) | ((o & 1u) << 3));
+}
+
+
+/* ---- per-pass register networks (twiddle pointers are 64-bit so sub-block offsets fold into immediates) --- */
+
+__device__ __forceinline__ Mulc ld_tw(const uint4 *wu, const uint2 *qq, int off)
+{
+  const uint4 a = __ldg(wu + off);
+  const uint2 b = __ldg(qq + off);
+  return Mulc{a.x, a.y, a.z, a.w, b.x, b.y};
+}
+
+/*
+ * R-stage network on x[0..2^R) for a group whose first stage is global stage s0 and whose block index at that
+ * stage is blk0.  Forward: stages s0..s0+R-1, stage s0+u pairs x[k], x[k+d], d = 2^(R-1-u), sub-block `sub`
+ * uses twiddle 2^(s0+u) + (blk0<<u) + sub.  Inverse: same stages backwards, Gentleman-Sande, bound constants
+ * from p.inv_c[].  TOP_RENORM: this pass may be asked (p.inv_renorm_mask) to pull values below 3q first.
+ */
+template <int R, bool FWD>
+__device__ __forceinline__ void ring_network(uint64_t (&x)[1 << R], const ntt_cuda_params_t &p, uint32_t s0,
+                                             uint32_t blk0)
+{
+  constexpr int n = 1 << R;
+  const uint4 * wu = (const uint4 *)(FWD ? p.fwd_wu : p.inv_wu);
+  const uint2 * qq = (const uint2 *)(FWD ? p.fwd_qq : p.inv_qq);
+  if(FWD) {
+#pragma unroll
+    for(int u = 0; u < R; u++) {
+      const int    d   = n >> (u + 1);
+      const size_t idx = ((size_t)1 << (s0 + u)) + ((size_t)blk0 << u);
+#pragma unroll
+      for(int sub = 0; sub < (1 << u); sub++) {
+        const Mulc m = ld_tw(wu + idx, qq + idx, sub);
+#pragma unroll
+        for(int k = 0; k < d; k++) bfly_fwd<false>(x[sub * 2 * d + k], x[sub * 2 * d + k + d], m, p, p.c10q);
+      }
+    }
+  } else {
+#pragma unroll
+    for(int u = R - 1; u >= 0; u--) {
+      const int      d  = n >> (u + 1);
+      const uint32_t s  = s0 + u;
+      const uint64_t cb = p.inv_c[s];
+      if(u == R - 1 && ((p.inv_renorm_mask >> s) & 1u)) {
+        const Red rc{p.q, p.negq, p.red_shift, p.red_mu};
+#pragma unroll
+        for(int k = 0; k < n; k++) x[k] = reduce_3q(x[k], rc);
+      }
+      if(u == 0 && s == 0) {
+        const Mulc a = mulc_from(p.ninv), b = mulc_from(p.ninv_w1);
+#pragma unroll
+        for(int k = 0; k < d; k++) bfly_inv_final<false>(x[k], x[k + d], a, b, p, cb);
+      } else {
+        const size_t idx = ((size_t)1 << s) + ((size_t)blk0 << u);
+#pragma unroll
+        for(int sub = 0; sub < (1 << u); sub++) {
+          const Mulc m = ld_tw(wu + idx, qq + idx, sub);
+#pragma unroll
+          for(int k = 0; k < d; k++) bfly_inv<false>(x[sub * 2 * d + k], x[sub * 2 * d + k + d], m, p, cb);
+        }
+      }
+    }
+  }
+}
+
+/* Pass C network: the last four stages on 16 contiguous coefficients, twiddles from the [15][groups]
+ * table: entry t = 2^u-1+sub of group gidx sits at t*groups + gidx. */
+template <bool FWD>
+__device__ __forceinline__ void ring_network_c(uint64_t (&x)[16], const ntt_cuda_params_t &p, uint32_t s0,
+                                               size_t gidx, size_t groups)
+{
+  const uint4 *wu = (const uint4 *)(FWD ? p.fwd_ct_wu : p.inv_ct_wu) + gidx;
+  const uint2 *qq = (const uint2 *)(FWD ? p.fwd_ct_qq : p.inv_ct_qq) + gidx;
+  if(FWD) {
+#pragma unroll
+    for(int u = 0; u < 4; u++) {
+      const int d = 8 >> u;
+#pragma unroll
+      for(int sub = 0; sub < (1 << u); sub++) {
+        const size_t t = (size_t)((1 << u) - 1 + sub) * groups;
+        const Mulc   m = ld_tw(wu + t, qq + t, 0);
+#pragma unroll
+        for(int k = 0; k < d; k++) bfly_fwd<false>(x[sub * 2 * d + k], x[sub * 2 * d + k + d], m, p, p.c10q);
+      }
+    }
+  } else {
+#pragma unroll
+    for(int u = 3; u >= 0; u--) {
+      const int      d  = 8 >> u;
+      const uint32_t s  = s0 + u;
+      const uint64_t cb = p.inv_c[s];
+      if(u == 3 && ((p.inv_renorm_mask >> s) & 1u)) {
+        const Red rc{p.q, p.negq, p.red_shift, p.red_mu};
+#pragma unroll
+        for(int k = 0; k < 16; k++) x[k] = reduce_3q(x[k], rc);
+      }
+#pragma unroll
+      for(int sub = 0; sub < (1 << u); sub++) {
+        const size_t t = (size_t)((1 << u) - 1 + sub) * groups;
+        const Mulc   m = ld_tw(wu + t, qq + t, 0);
+#pragma unroll
+        for(int k = 0; k < d; k++) bfly_inv<false>(x[sub * 2 * d + k], x[sub * 2 * d + k + d], m, p, cb);
+      }
+    }
+  }
+}
+
+/* ---- the kernel ----------------------------------------------------------------------------------------------- */
+
+template <int L, bool FWD>
+__global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
+  k_ring(const __grid_constant__ ntt_cuda_params_t p, const __grid_constant__ CUtensorMap tmap, size_t n_chunks)
+{
+  using C = RingCfg<L>;
+  constexpr int NB = C::NB, RA = C::RA, SLOTS = C::SLOTS, T = C::THREADS, HALF = NB / 2;
+  extern __shared__ uint8_t smem_raw[];
+  /* slots need 1024-byte alignment for SWIZZLE_128B; barriers sit behind the ring */
+  const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = ring + SLOTS * 4096;
+  uint8_t *      ring_ptr = smem_raw + (ring - smem_u32(smem_raw));
+
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t s1       = p.logn - L;                       /* stages already done by strided passes */
+  const size_t   my_polys = (n_chunks > blockIdx.x) ? (n_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const size_t   my_blocks = my_polys * NB;
+  const size_t   groups   = (size_t)1 << (p.logn - 4);        /* 16-coefficient runs per polynomial */
+
+  auto slot_addr = [&](size_t g) -> uint32_t { return ring + (uint32_t)(g % SLOTS) * 4096u; };
+  /* arm + issue the TMA load of block g of this CTA's sequence (no-op past the end) */
+  auto issue_load = [&](size_t g) {
+    if(g >= my_blocks) return;
+    const size_t   k     = g / NB;
+    const uint32_t b     = (uint32_t)(g % NB);
+    const size_t   chunk = blockIdx.x + k * gridDim.x;
+    const uint32_t bar   = bars + 8u * (uint32_t)(k % C::NBAR);
+    mbar_arrive_expect_tx(bar, 4096u);
+    tma_load_block(slot_addr(g), &tmap, (int)((chunk << (L - 4)) + b * 32u), bar);
+  };
+
+  if(tid == 0) {
+    tma_prefetch_desc(&tmap);
+    for(int i = 0; i < C::NBAR; i++) mbar_init(bars + 8u * i, NB);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  /* prologue: fill the ring */
+  for(uint32_t g = tid; g < (uint32_t)SLOTS; g += T) issue_load(g);
+
+  for(size_t k = 0; k < my_polys; k++) {
+    const size_t   chunk = blockIdx.x + k * gridDim.x;
+    const uint32_t cp    = (uint32_t)(chunk & (((size_t)1 << s1) - 1)); /* chunk index inside its polynomial */
+    const size_t   g0    = k * NB;
+    const uint32_t sl0   = (uint32_t)(g0 % SLOTS);
+    mbar_wait(bars + 8u * (uint32_t)(k % C::NBAR), (uint32_t)((k / C::NBAR) & 1));
+
+    /* slot of block b of this polynomial (uniform arithmetic: one compare per block) */
+    auto blk_slot = [&](uint32_t b) -> uint32_t {
+      uint32_t s = sl0 + b;
+      return s >= (uint32_t)SLOTS ? s - SLOTS : s;
+    };
+
+    /* ---------- pass A (forward first, inverse last): across blocks ---------- */
+    auto pass_a = [&]() {
+      for(uint32_t j = tid; j < 512u; j += T) {
+        const uint32_t off = slot_off(j);
+        uint64_t       x[NB];
+#pragma unroll
+        for(int b = 0; b < NB; b++) x[b] = *reinterpret_cast<const uint64_t *>(ring_ptr + blk_slot(b) * 4096u + off);
+        ring_network<RA, FWD>(x, p, s1, cp);
+        if(!FWD && s1 == 0) {
+          const Red rc{p.q, p.negq, p.red_shift, p.red_mu};
+#pragma unroll
+          for(int b = 0; b < NB; b++) x[b] = reduce_full(x[b], rc);
+        }
+#pragma unroll
+        for(int b = 0; b < NB; b++) *reinterpret_cast<uint64_t *>(ring_ptr + blk_slot(b) * 4096u + off) = x[b];
+      }
+    };
+
+    /* ---------- pass B: inside a block, 32 coefficients at stride 16; half-warp h owns block warp + h*HALF ---- */
+    const uint32_t hb   = lane >> 4, jb = lane & 15u;
+    const uint32_t blkB = warp + hb * HALF;
+    auto pass_b = [&]() {
+      uint8_t *      base = ring_ptr + blk_slot(blkB) * 4096u + ((jb & 1u) << 3);
+      const uint32_t jc   = jb >> 1;
+      uint64_t       x[32];
+#pragma unroll
+      for(int kk = 0; kk < 32; kk++)
+        x[kk] = *reinterpret_cast<const uint64_t *>(base + kk * 128 + ((jc ^ (uint32_t)(kk & 7)) << 4));
+      ring_network<5, FWD>(x, p, s1 + RA, cp * NB + blkB);
+#pragma unroll
+      for(int kk = 0; kk < 32; kk++)
+        *reinterpret_cast<uint64_t *>(base + kk * 128 + ((jc ^ (uint32_t)(kk & 7)) << 4)) = x[kk];
+    };
+
+    /* ---------- pass C: one swizzled 128-byte row (16 contiguous coefficients) per lane ---------- */
+    auto pass_c = [&](uint32_t blk) {
+      uint8_t *base = ring_ptr + blk_slot(blk) * 4096u + lane * 128u;
+      uint64_t x[16];
+#pragma unroll
+      for(int c = 0; c < 8; c++) {
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(base + (((uint32_t)c ^ (lane & 7u)) << 4));
+        x[2 * c]           = v.x;
+        x[2 * c + 1]       = v.y;
+      }
+      ring_network_c<FWD>(x, p, s1 + RA + 5, ((size_t)cp * NB + blk) * 32 + lane, groups);
+      if(FWD) {
+        const Red rc{p.q, p.negq, p.red_shift, p.red_mu};
+#pragma unroll
+        for(int i = 0; i < 16; i++) x[i] = reduce_full(x[i], rc);
+      }
+#pragma unroll
+      for(int c = 0; c < 8; c++) {
+        ulonglong2 v;
+        v.x = x[2 * c];
+        v.y = x[2 * c + 1];
+        *reinterpret_cast<ulonglong2 *>(base + (((uint32_t)c ^ (lane & 7u)) << 4)) = v;
+      }
+    };
+
+    /* store block b of this polynomial from its slot (called by one lane after fence + warp sync) */
+    auto store_block = [&](uint32_t b) {
+      tma_store_block(&tmap, (int)((chunk << (L - 4)) + b * 32u), ring + blk_slot(b) * 4096u);
+      tma_commit();
+    };
+
+    if(FWD) {
+      pass_a();
+      __syncthreads();
+      pass_b();
+      __syncwarp();
+      pass_c(warp);
+      fence_proxy_async();
+      __syncwarp();
+      if(lane == 0) store_block(warp);
+      pass_c(warp + HALF);
+      fence_proxy_async();
+      __syncwarp();
+      if(lane == 0) {
+        store_block(warp + HALF);
+        /* both slots are re-armed once the stores have drained them */
+        tma_wait_read_all();
+        issue_load(g0 + warp + SLOTS);
+        issue_load(g0 + warp + HALF + SLOTS);
+      }
+      __syncwarp();
+    } else {
+      pass_c(warp);
+      pass_c(warp + HALF);
+      __syncwarp();
+      pass_b();
+      __syncthreads();
+      pass_a();
+      fence_proxy_async();
+      __syncthreads();
+      if(tid < (uint32_t)NB) {
+        store_block(tid);
+        tma_wait_read_all();
+        issue_load(g0 + tid + SLOTS);
+      }
+    }
+  }
+  /* the kernel may not exit while its bulk stores are still in flight */
+  tma_wait_all();
+}
+
+}  // namespace nttb200

@@ -17,7 +17,7 @@
 
 typedef unsigned __int128 u128;
 
-#define LAZY_MAX_QBITS 56 /* lazy path needs (4 + 6*24) * q < 2^64 */
+#define LAZY_MAX_QBITS 56 /* lazy path needs (4 + 10*24) * q < 2^64 */
 #define HOST_PIPE_DEPTH 3
 #define HOST_PIPE_BYTES ((size_t)32 << 20)
 
@@ -30,6 +30,7 @@ struct ntt_b200_plan {
   ntt_cuda_params_t params;
   /* device memory: kernel tables and the reference-format copies kept for export */
   void *    d_fwd_wu, *d_fwd_qq, *d_inv_wu, *d_inv_qq;
+  void *    d_fwd_ct_wu, *d_fwd_ct_qq, *d_inv_ct_wu, *d_inv_ct_qq; /* pass-C layout of the last four stages */
   uint64_t *d_w, *d_w_con, *d_w_inv, *d_w_inv_con;
   /* host-buffer pipeline (created on first use) */
   pthread_mutex_t pipe_lock;
@@ -68,8 +69,8 @@ static ntt_cuda_mulc_t make_mulc(uint64_t w, uint64_t q, int lazy)
     const uint64_t u = (uint64_t)((((u128)w) << 32) % q);
     m.u0             = (uint32_t)u;
     m.u1             = (uint32_t)(u >> 32);
-    m.wq             = (uint32_t)nttm_shoup(w, q, 31);
-    m.uq             = (uint32_t)nttm_shoup(u, q, 31);
+    m.wq             = (uint32_t)nttm_shoup(w, q, 30);
+    m.uq             = (uint32_t)nttm_shoup(u, q, 30);
   } else {
     const uint64_t c = nttm_shoup(w, q, 64);
     m.u0             = (uint32_t)c;
@@ -96,6 +97,7 @@ static void fill_params(ntt_b200_plan_t *pl)
   p->q         = pl->q;
   p->neg2q     = (uint64_t)0 - 2 * pl->q;
   p->negq      = (uint64_t)0 - pl->q;
+  p->c10q      = 10 * pl->q;
   p->logn      = pl->logn;
   p->lazy      = nttm_bitlen(pl->q) <= LAZY_MAX_QBITS ? 1u : 0u;
   p->red_shift = nttm_bitlen(pl->q) - 1;
@@ -105,8 +107,9 @@ static void fill_params(ntt_b200_plan_t *pl)
 static void plan_free(ntt_b200_plan_t *pl)
 {
   if(!pl) return;
-  void *dev_ptrs[] = {pl->d_fwd_wu, pl->d_fwd_qq, pl->d_inv_wu, pl->d_inv_qq,
-                      pl->d_w,      pl->d_w_con,  pl->d_w_inv,  pl->d_w_inv_con};
+  void *dev_ptrs[] = {pl->d_fwd_wu,    pl->d_fwd_qq,    pl->d_inv_wu,    pl->d_inv_qq, pl->d_w,    pl->d_w_con,
+                      pl->d_w_inv,     pl->d_w_inv_con, pl->d_fwd_ct_wu, pl->d_fwd_ct_qq, pl->d_inv_ct_wu,
+                      pl->d_inv_ct_qq};
   for(size_t i = 0; i < sizeof(dev_ptrs) / sizeof(dev_ptrs[0]); i++) {
     if(dev_ptrs[i]) ntt_cuda_free(pl->device, dev_ptrs[i]);
   }
@@ -143,6 +146,29 @@ static int build_direction(ntt_b200_plan_t *pl, const uint64_t *d_w, void **wu, 
   return NTT_B200_SUCCESS;
 }
 
+/* pass-C copies of the last four stages (lazy path, N >= 2^12: the sizes the ring kernel serves) */
+static int build_ctables(ntt_b200_plan_t *pl, const void *wu, const void *qq, void **ct_wu, void **ct_qq)
+{
+  if(!pl->params.lazy || pl->logn < 12) return NTT_B200_SUCCESS;
+  const size_t entries = (size_t)15 << (pl->logn - 4);
+  if(ntt_cuda_malloc(pl->device, ct_wu, entries * 16) || ntt_cuda_malloc(pl->device, ct_qq, entries * 8))
+    return cuda_error("table alloc");
+  if(ntt_cuda_build_ctables(pl->device, &pl->params, wu, qq, *ct_wu, *ct_qq, NULL)) return cuda_error("table build");
+  return NTT_B200_SUCCESS;
+}
+
+static void publish_tables(ntt_b200_plan_t *pl)
+{
+  pl->params.fwd_wu    = pl->d_fwd_wu;
+  pl->params.fwd_qq    = pl->d_fwd_qq;
+  pl->params.inv_wu    = pl->d_inv_wu;
+  pl->params.inv_qq    = pl->d_inv_qq;
+  pl->params.fwd_ct_wu = pl->d_fwd_ct_wu;
+  pl->params.fwd_ct_qq = pl->d_fwd_ct_qq;
+  pl->params.inv_ct_wu = pl->d_inv_ct_wu;
+  pl->params.inv_ct_qq = pl->d_inv_ct_qq;
+}
+
 static int finish_inverse_constants(ntt_b200_plan_t *pl, uint64_t w_inv_1)
 {
   const int lazy      = (int)pl->params.lazy;
@@ -160,6 +186,8 @@ static int adopt_table(ntt_b200_plan_t *pl, const uint64_t *w, const uint64_t *w
   if(ntt_cuda_malloc(pl->device, (void **)d_w, bytes)) return cuda_error("table alloc");
   if(ntt_cuda_h2d(pl->device, *d_w, w, bytes, NULL)) return cuda_error("table upload");
   int rc = build_direction(pl, *d_w, wu, qq, d_con);
+  if(!rc) rc = (wu == &pl->d_fwd_wu) ? build_ctables(pl, *wu, *qq, &pl->d_fwd_ct_wu, &pl->d_fwd_ct_qq)
+                                     : build_ctables(pl, *wu, *qq, &pl->d_inv_ct_wu, &pl->d_inv_ct_qq);
   if(rc) return rc;
   if(w_con) {
     uint64_t *chk = malloc(bytes);
@@ -214,11 +242,8 @@ int ntt_b200_plan_create(ntt_b200_plan_t **plan, int device, uint64_t N, uint64_
     plan_free(pl);
     return rc;
   }
-  pl->params.fwd_wu = pl->d_fwd_wu;
-  pl->params.fwd_qq = pl->d_fwd_qq;
-  pl->params.inv_wu = pl->d_inv_wu;
-  pl->params.inv_qq = pl->d_inv_qq;
-  *plan             = pl;
+  publish_tables(pl);
+  *plan = pl;
   return NTT_B200_SUCCESS;
 }
 
@@ -245,6 +270,8 @@ int ntt_b200_plan_create_psi(ntt_b200_plan_t **plan, int device, uint64_t N, uin
   }
   if(!rc) rc = build_direction(pl, pl->d_w, &pl->d_fwd_wu, &pl->d_fwd_qq, &pl->d_w_con);
   if(!rc) rc = build_direction(pl, pl->d_w_inv, &pl->d_inv_wu, &pl->d_inv_qq, &pl->d_w_inv_con);
+  if(!rc) rc = build_ctables(pl, pl->d_fwd_wu, pl->d_fwd_qq, &pl->d_fwd_ct_wu, &pl->d_fwd_ct_qq);
+  if(!rc) rc = build_ctables(pl, pl->d_inv_wu, pl->d_inv_qq, &pl->d_inv_ct_wu, &pl->d_inv_ct_qq);
   if(!rc && ntt_cuda_sync(device, NULL)) rc = cuda_error("table generation");
   /* w_inv[1] = psi_inv^(N/2) */
   if(!rc) rc = finish_inverse_constants(pl, nttm_powmod(psi_inv, N / 2, q));
@@ -253,11 +280,8 @@ int ntt_b200_plan_create_psi(ntt_b200_plan_t **plan, int device, uint64_t N, uin
     return rc;
   }
   pl->has_fwd = pl->has_inv = 1;
-  pl->params.fwd_wu = pl->d_fwd_wu;
-  pl->params.fwd_qq = pl->d_fwd_qq;
-  pl->params.inv_wu = pl->d_inv_wu;
-  pl->params.inv_qq = pl->d_inv_qq;
-  *plan             = pl;
+  publish_tables(pl);
+  *plan = pl;
   return NTT_B200_SUCCESS;
 }
 
