@@ -33,7 +33,7 @@ typedef struct ntt_cuda_params {
   uint64_t c10q;    /* 10q: bound of a lazy product, added to keep differences non-negative */
   uint32_t logn;
   uint32_t lazy;    /* 1: lazy split-multiplier path, 0: exact Harvey path */
-  uint32_t red_shift; /* final reduction: vt = v >> red_shift, Q = hi32(vt * red_mu) */
+  uint32_t red_shift; /* reduction: vt = v >> red_shift, Q = hi32(vt * red_mu); shift = max(0, bitlen(q)-9) */
   uint32_t red_mu;
   /* forward twiddles: wu[N] (uint4: w0,w1,u0,u1) and qq[N] (uint2: wq,uq), reference index order */
   const void *fwd_wu;
@@ -52,7 +52,7 @@ typedef struct ntt_cuda_params {
   /* inverse lazy bookkeeping, indexed by global stage s (processed m-1 .. 0):
    * inv_c[s] = B_s * q with B_s the value bound (in units of q) before stage s */
   uint64_t inv_c[NTT_MAX_STAGES];
-  uint32_t inv_renorm_mask; /* bit s set: bring values below 3q before running stage s */
+  uint32_t inv_renorm_mask; /* bit s set: bring values below 2q before running stage s */
 } ntt_cuda_params_t;
 
 const char *ntt_cuda_error(void);

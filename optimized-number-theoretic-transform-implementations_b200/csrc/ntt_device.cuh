@@ -102,16 +102,22 @@ __device__ __forceinline__ uint64_t mul_exact(uint64_t y, const Mulc &m, uint64_
   return w * y - mulhi64(c, y) * q;
 }
 
-__device__ __forceinline__ uint64_t csub(uint64_t v, uint64_t m) { return v >= m ? v - m : v; }
+/* v - m if v >= m else v, for v, m < 2^63 (sign test of the difference: 2 adds, 1 compare, 2 selects) */
+__device__ __forceinline__ uint64_t csub(uint64_t v, uint64_t m)
+{
+  const uint64_t t = v - m;
+  return ((int64_t)t < 0) ? v : t;
+}
 
-struct Red {  // final-reduction constants
+struct Red {  // reduction constants
   uint64_t q, negq;
   uint32_t shift, mu;
 };
 
-/* v < 2^(shift+32)  ->  v mod q up to a multiple: result in [0,3q).  shift = bitlen(q)-1,
- * mu = floor(2^(32+shift)/q).  4 instructions (1 funnel shift, 3 IMAD). */
-__device__ __forceinline__ uint64_t reduce_3q(uint64_t v, const Red &c)
+/* v < 2^(bitlen(q)+22)  ->  v mod q up to one multiple: result in [0,2q).
+ * shift = max(0, bitlen(q)-9), mu = floor(2^(32+shift)/q) < 2^24: the quotient estimate
+ * Q = floor(floor(v/2^shift) * mu / 2^32) is floor(v/q) or one less.  1 funnel shift + 3 IMAD. */
+__device__ __forceinline__ uint64_t reduce_2q(uint64_t v, const Red &c)
 {
   const uint32_t vt = (uint32_t)(v >> c.shift);
   const uint32_t Q  = hi32(mul_wide(vt, c.mu));
@@ -119,10 +125,7 @@ __device__ __forceinline__ uint64_t reduce_3q(uint64_t v, const Red &c)
   return pack64(lo32(r), mad_lo(Q, hi32(c.negq), hi32(r)));
 }
 /* v -> v mod q in [0,q) */
-__device__ __forceinline__ uint64_t reduce_full(uint64_t v, const Red &c)
-{
-  return csub(csub(reduce_3q(v, c), c.q), c.q);
-}
+__device__ __forceinline__ uint64_t reduce_full(uint64_t v, const Red &c) { return csub(reduce_2q(v, c), c.q); }
 
 __device__ __forceinline__ Mulc load_mulc(const uint4 *wu, const uint2 *qq, uint32_t idx)
 {
@@ -143,8 +146,8 @@ __device__ __forceinline__ Mulc mulc_from(const ntt_cuda_mulc_t &m)
 /* ---- butterflies -------------------------------------------------------------------------------- */
 
 /* forward (Cooley-Tukey) butterfly, harvey_fwd_butterfly fast_mul_operators.h:72-81.
- * lazy: X' = X + T, Y' = X - T + 10q with T in [0,10q): both outputs < X + 10q.  X' comes straight out of
- * the multiply-accumulate chain (X is its addend) and Y' = 2X + 10q - X'. */
+ * lazy: X' = X + T, Y' = X - T + 10q with T in [0,10q): both outputs < X + 10q.  (ptxas sums the three
+ * 64-bit partial products with one 3-input add pair either way, so T is formed first: 6 add instructions.) */
 template <bool EXACT>
 __device__ __forceinline__ void bfly_fwd(uint64_t &x, uint64_t &y, const Mulc &m, const ntt_cuda_params_t &p,
                                          uint64_t c10q)
@@ -156,9 +159,9 @@ __device__ __forceinline__ void bfly_fwd(uint64_t &x, uint64_t &y, const Mulc &m
     x                 = x1 + t;
     y                 = x1 - t + q2;
   } else {
-    const uint64_t xs = mul_lazy_acc(y, m, p.neg2q, x);
-    y                 = (x + x + c10q) - xs;
-    x                 = xs;
+    const uint64_t t = mul_lazy(y, m, p.neg2q);
+    y                = x - t + c10q;
+    x                = x + t;
   }
 }
 

@@ -124,7 +124,7 @@ __device__ __forceinline__ void radix_network(uint64_t (&x)[1 << R], const ntt_c
       if(!EXACT && u == R - 1 && ((p.inv_renorm_mask >> s) & 1u)) {
         const Red rc{p.q, p.negq, p.red_shift, p.red_mu};
 #pragma unroll
-        for(int k = 0; k < n; k++) x[k] = reduce_3q(x[k], rc);
+        for(int k = 0; k < n; k++) x[k] = reduce_2q(x[k], rc);
       }
       if(u == 0 && s == 0) {
         /* global stage 0 (only reachable with blk0 == 0, u == 0): N^-1 folded in */
@@ -146,7 +146,7 @@ __device__ __forceinline__ void radix_network(uint64_t (&x)[1 << R], const ntt_c
 template <bool EXACT>
 __device__ __forceinline__ uint64_t finish(uint64_t v, const ntt_cuda_params_t &p)
 {
-  if(EXACT) return csub(csub(v, p.q << 1), p.q);
+  if(EXACT) return csub(csub(v, p.q << 1), p.q); /* 4q < 2^64 and q < 2^62: differences stay below 2^63 */
   const Red rc{p.q, p.negq, p.red_shift, p.red_mu};
   return reduce_full(v, rc);
 }
@@ -711,7 +711,7 @@ static Split make_split(int logn)
 
 /* Inverse lazy bookkeeping (see ntt_cuda.h): walks the passes in the order the inverse runs them and
  * records, per global stage s, the bound constant inv_c[s] = B_s*q and where values must first be pulled
- * back below 3q so that neither x+y nor x-y+B_s*q can reach 2^63. */
+ * back below 2q so that neither x+y nor x-y+B_s*q can reach 2^63. */
 extern "C" int ntt_cuda_plan_inverse_bounds(ntt_cuda_params_t *p)
 {
   const int logn = (int)p->logn;
@@ -736,14 +736,16 @@ extern "C" int ntt_cuda_plan_inverse_bounds(ntt_cuda_params_t *p)
       rads[np++] = sp.r[k];
     }
   }
-  const long double lim = 9223372036854775808.0L; /* 2^63 */
-  long double       B   = 2.0L;                   /* input contract of the inverse: [0,2q) */
+  /* values must stay below 2^63 (x+y, x-y+B*q) and below 2^(bitlen(q)+22) (precondition of reduce_2q) */
+  long double lim = 9223372036854775808.0L / (long double)p->q; /* in units of q */
+  if(lim > 2097152.0L) lim = 2097152.0L;                         /* 2^21 */
+  long double B = 2.0L;                                          /* input contract of the inverse: [0,2q) */
   for(int k = 0; k < np; k++) {
-    if(B * (long double)(1u << rads[k]) * (long double)p->q >= lim) {
+    if(B * (long double)(1u << rads[k]) >= lim) {
       p->inv_renorm_mask |= 1u << tops[k];
-      B = 3.0L;
+      B = 2.0L;
     }
-    if(B * (long double)(1u << rads[k]) * (long double)p->q >= lim) return fail_msg("q too large for the lazy inverse");
+    if(B * (long double)(1u << rads[k]) >= lim) return fail_msg("q too large for the lazy inverse");
     for(int u = 0; u < rads[k]; u++) {
       const int s = tops[k] - u;
       p->inv_c[s] = (uint64_t)B * p->q;

@@ -5,8 +5,8 @@
  * of 512 coefficients (4 KiB).  Shared memory is a ring of SLOTS 4-KiB slots; block g of the CTA's work
  * sequence lives in slot g mod SLOTS.  Blocks arrive by TMA (cp.async.bulk.tensor, SWIZZLE_128B, one
  * mbarrier per polynomial-in-flight), results leave by TMA store straight out of the slot, and the slot is
- * re-armed with the block SLOTS positions further down the sequence.  With SLOTS = 56 at L = 14 the next
- * polynomial is (almost) completely resident before the current one finishes, so HBM traffic overlaps the
+ * re-armed with the block SLOTS positions further down the sequence.  With SLOTS = 50 at L = 14 most of the next
+ * polynomial is resident before the current one finishes, so HBM traffic overlaps the
  * butterflies without any register staging.
  *
  * Forward schedule for one chunk (stage numbers local to the chunk; the inverse mirrors it):
@@ -102,16 +102,21 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *tm)
 template <int L>
 struct RingCfg {
   static_assert(L >= 12 && L <= 14, "ring kernel covers chunks of 2^12 .. 2^14");
-  static constexpr int RA        = L - 9;                 /* stages of pass A */
-  static constexpr int NB        = 1 << RA;               /* 512-element blocks per chunk */
-  static constexpr int WARPS     = NB / 2 < 1 ? 1 : NB / 2;
-  static constexpr int THREADS   = WARPS * 32;
-  static constexpr int CTAS      = 512 / THREADS < 8 ? 512 / THREADS : 8; /* resident CTAs per SM */
-  /* ring depth: everything that fits next to the 1 KiB per-CTA system reservation (228 KiB per SM) */
-  static constexpr int SLOTS     = CTAS == 1 ? 56 : (CTAS == 2 ? 27 : 13);
-  static constexpr int NBAR      = 4;                     /* polynomials in flight (mbarrier ring) */
-  static constexpr int SMEM      = SLOTS * 4096 + 1024 /* alignment slack */ + 64 /* barriers */;
-  static constexpr int GROUPS_A  = 512;                   /* columns */
+  static constexpr int RA       = L - 9;                  /* stages of pass A */
+  static constexpr int NB       = 1 << RA;                /* 512-element blocks per chunk */
+  static constexpr int WARPS    = NB / 2;
+  static constexpr int THREADS  = WARPS * 32;
+  static constexpr int CTAS     = 512 / THREADS;          /* resident CTAs per SM (16 warps per SM) */
+  static constexpr int NBAR     = 4;                      /* polynomials in flight (mbarrier ring) */
+  /* shared-memory copy of the twiddles of passes A and B: NB-1 entries for pass A, 31 per block for pass B */
+  static constexpr int NTW      = NB - 1 + NB * 31;
+  static constexpr int TW_BYTES = ((NTW * 24 + 127) / 128) * 128;
+  /* 228 KiB per SM, 1 KiB reserved per resident CTA, at most 227 KiB per CTA */
+  static constexpr int PER_CTA  = 233472 / CTAS - 1024;
+  static constexpr int BUDGET   = PER_CTA < 232448 ? PER_CTA : 232448;
+  static constexpr int SLOTS    = (BUDGET - TW_BYTES - 1024 - 64) / 4096;  /* 50 / 24 / 12 for L = 14 / 13 / 12 */
+  static constexpr int SMEM     = SLOTS * 4096 + 1024 /* alignment slack */ + TW_BYTES + 64 /* barriers */;
+  static_assert(SLOTS > NB && 4 * NB > SLOTS, "ring depth vs. mbarrier reuse distance");
 };
 
 /* byte offset of coefficient o (0..511) inside a 4-KiB slot under TMA SWIZZLE_128B (rows of 128 bytes) */
@@ -130,6 +135,13 @@ __device__ __forceinline__ Mulc ld_tw(const uint4 *wu, const uint2 *qq, int off)
   const uint2 b = __ldg(qq + off);
   return Mulc{a.x, a.y, a.z, a.w, b.x, b.y};
 }
+/* same entry from the shared-memory twiddle cache (plain loads: LDS.128 + LDS.64) */
+__device__ __forceinline__ Mulc ld_tw_s(const uint4 *wu, const uint2 *qq, int off)
+{
+  const uint4 a = wu[off];
+  const uint2 b = qq[off];
+  return Mulc{a.x, a.y, a.z, a.w, b.x, b.y};
+}
 
 /*
  * R-stage network on x[0..2^R) for a group whose first stage is global stage s0 and whose block index at that
@@ -139,19 +151,17 @@ __device__ __forceinline__ Mulc ld_tw(const uint4 *wu, const uint2 *qq, int off)
  */
 template <int R, bool FWD>
 __device__ __forceinline__ void ring_network(uint64_t (&x)[1 << R], const ntt_cuda_params_t &p, uint32_t s0,
-                                             uint32_t blk0)
+                                             const uint4 *tw_wu, const uint2 *tw_qq)
 {
+  /* tw_wu / tw_qq: shared-memory twiddles of this group, entry 2^u-1+sub for stage s0+u, sub-block sub */
   constexpr int n = 1 << R;
-  const uint4 * wu = (const uint4 *)(FWD ? p.fwd_wu : p.inv_wu);
-  const uint2 * qq = (const uint2 *)(FWD ? p.fwd_qq : p.inv_qq);
   if(FWD) {
 #pragma unroll
     for(int u = 0; u < R; u++) {
-      const int    d   = n >> (u + 1);
-      const size_t idx = ((size_t)1 << (s0 + u)) + ((size_t)blk0 << u);
+      const int d = n >> (u + 1);
 #pragma unroll
       for(int sub = 0; sub < (1 << u); sub++) {
-        const Mulc m = ld_tw(wu + idx, qq + idx, sub);
+        const Mulc m = ld_tw_s(tw_wu, tw_qq, (1 << u) - 1 + sub);
 #pragma unroll
         for(int k = 0; k < d; k++) bfly_fwd<false>(x[sub * 2 * d + k], x[sub * 2 * d + k + d], m, p, p.c10q);
       }
@@ -165,17 +175,16 @@ __device__ __forceinline__ void ring_network(uint64_t (&x)[1 << R], const ntt_cu
       if(u == R - 1 && ((p.inv_renorm_mask >> s) & 1u)) {
         const Red rc{p.q, p.negq, p.red_shift, p.red_mu};
 #pragma unroll
-        for(int k = 0; k < n; k++) x[k] = reduce_3q(x[k], rc);
+        for(int k = 0; k < n; k++) x[k] = reduce_2q(x[k], rc);
       }
       if(u == 0 && s == 0) {
         const Mulc a = mulc_from(p.ninv), b = mulc_from(p.ninv_w1);
 #pragma unroll
         for(int k = 0; k < d; k++) bfly_inv_final<false>(x[k], x[k + d], a, b, p, cb);
       } else {
-        const size_t idx = ((size_t)1 << s) + ((size_t)blk0 << u);
 #pragma unroll
         for(int sub = 0; sub < (1 << u); sub++) {
-          const Mulc m = ld_tw(wu + idx, qq + idx, sub);
+          const Mulc m = ld_tw_s(tw_wu, tw_qq, (1 << u) - 1 + sub);
 #pragma unroll
           for(int k = 0; k < d; k++) bfly_inv<false>(x[sub * 2 * d + k], x[sub * 2 * d + k + d], m, p, cb);
         }
@@ -213,7 +222,7 @@ __device__ __forceinline__ void ring_network_c(uint64_t (&x)[16], const ntt_cuda
       if(u == 3 && ((p.inv_renorm_mask >> s) & 1u)) {
         const Red rc{p.q, p.negq, p.red_shift, p.red_mu};
 #pragma unroll
-        for(int k = 0; k < 16; k++) x[k] = reduce_3q(x[k], rc);
+        for(int k = 0; k < 16; k++) x[k] = reduce_2q(x[k], rc);
       }
 #pragma unroll
       for(int sub = 0; sub < (1 << u); sub++) {
@@ -237,8 +246,10 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
   extern __shared__ uint8_t smem_raw[];
   /* slots need 1024-byte alignment for SWIZZLE_128B; barriers sit behind the ring */
   const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bars = ring + SLOTS * 4096;
   uint8_t *      ring_ptr = smem_raw + (ring - smem_u32(smem_raw));
+  uint4 *        tw_wu = reinterpret_cast<uint4 *>(ring_ptr + SLOTS * 4096);       /* NTW x 16 bytes */
+  uint2 *        tw_qq = reinterpret_cast<uint2 *>(ring_ptr + SLOTS * 4096 + C::NTW * 16); /* NTW x 8 bytes */
+  const uint32_t bars  = ring + SLOTS * 4096 + C::TW_BYTES;
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t s1       = p.logn - L;                       /* stages already done by strided passes */
@@ -267,9 +278,33 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
   /* prologue: fill the ring */
   for(uint32_t g = tid; g < (uint32_t)SLOTS; g += T) issue_load(g);
 
+  uint32_t cached_cp = 0xffffffffu;
   for(size_t k = 0; k < my_polys; k++) {
     const size_t   chunk = blockIdx.x + k * gridDim.x;
     const uint32_t cp    = (uint32_t)(chunk & (((size_t)1 << s1) - 1)); /* chunk index inside its polynomial */
+    if(cp != cached_cp) {
+      /* (re)fill the pass A / pass B twiddle cache for this chunk position: pass A entry 2^u-1+sub is global
+       * 2^(s1+u) + (cp<<u) + sub; pass B, block b: 2^(s1+RA+u) + ((cp*NB+b)<<u) + sub.  When N = 2^L this
+       * happens once per CTA. */
+      const uint4 *gwu = (const uint4 *)(FWD ? p.fwd_wu : p.inv_wu);
+      const uint2 *gqq = (const uint2 *)(FWD ? p.fwd_qq : p.inv_qq);
+      __syncthreads();
+      for(uint32_t e = tid; e < (uint32_t)C::NTW; e += T) {
+        uint32_t t, st, blk;
+        if(e < (uint32_t)(NB - 1)) {
+          t = e; st = s1; blk = cp;
+        } else {
+          const uint32_t r = e - (NB - 1);
+          t = r % 31u; st = s1 + RA; blk = cp * NB + r / 31u;
+        }
+        const uint32_t u = 31u - __clz(t + 1u), sub = t + 1u - (1u << u);
+        const size_t   src = ((size_t)1 << (st + u)) + ((size_t)blk << u) + sub;
+        tw_wu[e] = __ldg(gwu + src);
+        tw_qq[e] = __ldg(gqq + src);
+      }
+      cached_cp = cp;
+      __syncthreads();
+    }
     const size_t   g0    = k * NB;
     const uint32_t sl0   = (uint32_t)(g0 % SLOTS);
     mbar_wait(bars + 8u * (uint32_t)(k % C::NBAR), (uint32_t)((k / C::NBAR) & 1));
@@ -287,7 +322,7 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
         uint64_t       x[NB];
 #pragma unroll
         for(int b = 0; b < NB; b++) x[b] = *reinterpret_cast<const uint64_t *>(ring_ptr + blk_slot(b) * 4096u + off);
-        ring_network<RA, FWD>(x, p, s1, cp);
+        ring_network<RA, FWD>(x, p, s1, tw_wu, tw_qq);
         if(!FWD && s1 == 0) {
           const Red rc{p.q, p.negq, p.red_shift, p.red_mu};
 #pragma unroll
@@ -308,7 +343,7 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
 #pragma unroll
       for(int kk = 0; kk < 32; kk++)
         x[kk] = *reinterpret_cast<const uint64_t *>(base + kk * 128 + ((jc ^ (uint32_t)(kk & 7)) << 4));
-      ring_network<5, FWD>(x, p, s1 + RA, cp * NB + blkB);
+      ring_network<5, FWD>(x, p, s1 + RA, tw_wu + (NB - 1) + blkB * 31, tw_qq + (NB - 1) + blkB * 31);
 #pragma unroll
       for(int kk = 0; kk < 32; kk++)
         *reinterpret_cast<uint64_t *>(base + kk * 128 + ((jc ^ (uint32_t)(kk & 7)) << 4)) = x[kk];

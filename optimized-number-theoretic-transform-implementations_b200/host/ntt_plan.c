@@ -100,7 +100,7 @@ static void fill_params(ntt_b200_plan_t *pl)
   p->c10q      = 10 * pl->q;
   p->logn      = pl->logn;
   p->lazy      = nttm_bitlen(pl->q) <= LAZY_MAX_QBITS ? 1u : 0u;
-  p->red_shift = nttm_bitlen(pl->q) - 1;
+  p->red_shift = nttm_bitlen(pl->q) > 9 ? nttm_bitlen(pl->q) - 9 : 0;
   p->red_mu    = (uint32_t)((((u128)1) << (32 + p->red_shift)) / pl->q);
 }
 

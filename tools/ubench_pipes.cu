@@ -52,6 +52,23 @@ __global__ void __launch_bounds__(1024) k(uint64_t* out, uint32_t seed, P p) {
         c[i] = ((uint64_t)rh << 32) | (uint32_t)r;
       }
       if (OP == 9) asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(c[i]) : "r"((uint32_t)c[i]), "r"(b[i]));
+      if (OP == 10) { asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b[i]), "r"(seed));
+                      asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(b[i]) : "r"(seed), "r"(seed)); }
+      if (OP == 11) { asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c[i]) : "r"(a[i]), "r"(b[i]));
+                      asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(b[i]) : "r"(seed), "r"(seed)); }
+      if (OP == 12) { asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c[i]) : "r"(a[i]), "r"(b[i]));
+                      asm volatile("add.cc.u32 %0, %0, %2; addc.u32 %1, %1, %3;" : "+r"(a[i]), "+r"(b[i]) : "r"(seed), "r"(seed + 1)); }
+      if (OP == 13) { uint64_t t; asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(t) : "r"(a[i]), "r"(b[i])); c[i] ^= t; }
+      if (OP == 14) { asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b[i]), "r"(seed));
+                      asm volatile("fma.rn.f64 %0, %0, %1, %1;" : "+d"(d[i]) : "d"(1.0000001)); }
+      if (OP == 15) { asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b[i]), "r"(seed));
+                      asm volatile("fma.rn.f64 %0, %0, %1, %1;" : "+d"(d[i]) : "d"(1.0000001)); }
+      if (OP == 16) { asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b[i]), "r"(seed));
+                      asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(b[i]) : "r"(seed), "r"(seed));
+                      asm volatile("fma.rn.f64 %0, %0, %1, %1;" : "+d"(d[i]) : "d"(1.0000001)); }
+      if (OP == 17) { float f = __uint_as_float(a[i]); asm volatile("fma.rn.f32 %0, %0, %1, %1;" : "+f"(f) : "f"(1.0001f)); a[i] = __float_as_uint(f); }
+      if (OP == 18) { float f = __uint_as_float(a[i]); asm volatile("fma.rn.f32 %0, %0, %1, %1;" : "+f"(f) : "f"(1.0001f)); a[i] = __float_as_uint(f);
+                      asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(b[i]) : "r"(seed), "r"(seed)); }
     }
   }
   uint64_t s = 0;
@@ -101,5 +118,14 @@ int main() {
   run<6>("shf", 1);
   run<7>("shoup64 exact modmul", 1);
   run<8>("approx9 modmul", 1);
+  run<10>("IMAD + LOP3 (2 instr)", 2);
+  run<11>("IMAD.WIDE + LOP3 (2 instr)", 2);
+  run<12>("IMAD.WIDE + IADD3 x2 (3 instr)", 3);
+  run<13>("mul.wide + 2 lop3 (3 instr)", 3);
+  run<14>("IMAD + DFMA (2 instr)", 2);
+  run<15>("LOP3 + DFMA (2 instr)", 2);
+  run<16>("IMAD + LOP3 + DFMA (3 instr)", 3);
+  run<17>("FFMA", 1);
+  run<18>("FFMA + IMAD (2 instr)", 2);
   return 0;
 }
