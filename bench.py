@@ -242,12 +242,25 @@ def load_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def load_compute_bound(fwd_ntt_per_s):
+    """The integer-pipe roofline of the butterfly (register-only microbenchmark tools/ubench_bfly.cu, result
+    committed in profiles/traffic.json): north_star's roofline is the slower of HBM and this."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            t = json.load(fh)
+        peak = float(t["int_pipe_bfly_per_s"]) / float(t["bfly_per_fwd_ntt_logn14"])
+        return {"bound": "integer pipe (IMAD)", "peak_ntt_per_s": peak, "achieved_ntt_per_s": fwd_ntt_per_s,
+                "frac": fwd_ntt_per_s / peak, "source": t.get("int_pipe_source")}
+    except Exception:
+        return None
+
+
 def load_traffic(logn):
     """dram bytes per launch of the forward chunk kernel from the committed ncu capture, or None."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
             t = json.load(fh)
-        return t.get("fwd_logn%d_bytes_per_ntt" % logn)
+        return t.get("fwd_logn%d_dram_bytes_per_ntt" % logn)
     except Exception:
         return None
 
@@ -340,10 +353,11 @@ def run_b200_arm(args):
     achieved = alg_bytes / (fwd_ms * 1e-3) / 1e9
     traffic = load_traffic(args.logn)
     roofline = {
-        "bound": "hbm", "kernel": "k_chunk<%d,fwd> (one launch = %d transforms)" % (args.logn, batch),
+        "bound": "hbm", "kernel": "k_ring<%d,fwd> (one launch = %d transforms)" % (args.logn, batch),
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": None if traffic is None else traffic * batch, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": fwd_ms,
+        "compute_bound": load_compute_bound(batch / (fwd_ms * 1e-3)),
         "inverse": {"kernel_ms": inv_ms, "achieved": alg_bytes / (inv_ms * 1e-3) / 1e9,
                     "frac": alg_bytes / (inv_ms * 1e-3) / 1e9 / peak},
         "fwd_ntt_per_s_per_gpu": batch / (fwd_ms * 1e-3), "inv_ntt_per_s_per_gpu": batch / (inv_ms * 1e-3),
