@@ -43,6 +43,13 @@ const char *ntt_b200_last_error(void);
 int ntt_b200_device_count(void);
 /* "ntt_b200 <version> sm_100a" */
 const char *ntt_b200_version(void);
+/*
+ * Kernel selection, for benchmarks and A/B parity tests only (every choice is a CUDA path):
+ *   "ring" 0/1  persistent TMA ring kernel for chunks of 2^12..2^14 (default 1; 0 = generic smem kernel)
+ *   "fp64" 0/1  run the ring kernel's butterflies on the FP64 pipe when q <= 2^49-1024 (default 1)
+ * The same switches are read from NTT_B200_NO_RING=1 / NTT_B200_NO_FP64=1 at first use.
+ */
+int ntt_b200_configure(const char *key, int value);
 
 /* ---- plans ---------------------------------------------------------------------------------------- */
 

@@ -41,6 +41,7 @@ def _bind():
     L.ntt_b200_last_error.restype = C.c_char_p
     L.ntt_b200_version.restype = C.c_char_p
     L.ntt_b200_device_count.restype = i
+    L.ntt_b200_configure.argtypes = [C.c_char_p, i]
     L.ntt_b200_plan_create.argtypes = [C.POINTER(vp), i, u64, u64, vp, vp, vp, vp, u64, u64]
     L.ntt_b200_plan_create_psi.argtypes = [C.POINTER(vp), i, u64, u64, u64]
     L.ntt_b200_plan_destroy.argtypes = [vp]
@@ -88,7 +89,7 @@ lib = _bind()
 
 #: every symbol include/ntt_b200.h declares (checked against the header and the .so by the CPU tests)
 EXPORTS = [
-    "ntt_b200_last_error", "ntt_b200_device_count", "ntt_b200_version",
+    "ntt_b200_last_error", "ntt_b200_device_count", "ntt_b200_version", "ntt_b200_configure",
     "ntt_b200_plan_create", "ntt_b200_plan_create_psi", "ntt_b200_plan_destroy",
     "ntt_b200_plan_n", "ntt_b200_plan_q", "ntt_b200_plan_device", "ntt_b200_plan_is_lazy",
     "ntt_b200_plan_export_tables",
@@ -116,6 +117,11 @@ def device_count():
 
 def version():
     return lib.ntt_b200_version().decode()
+
+
+def configure(key, value):
+    """Kernel selection for benchmarks / A-B tests: configure("fp64", 0), configure("ring", 0)."""
+    _check(lib.ntt_b200_configure(key.encode(), int(value)), "configure")
 
 
 def _ptr(x):

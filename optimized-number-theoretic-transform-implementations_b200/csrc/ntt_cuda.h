@@ -46,6 +46,16 @@ typedef struct ntt_cuda_params {
   const void *fwd_ct_qq;
   const void *inv_ct_wu;
   const void *inv_ct_qq;
+  /* FP64 path (q < 2^49, ntt_ring_fp.cuh): twiddles as (w, RN(w/q)) pairs of doubles, same index order as
+   * wu/qq, plus their pass-C re-layout; q and RN(1/q); N^-1 and N^-1*w_inv[1] in the same form */
+  uint32_t    fp64;
+  uint32_t    pad0;
+  double      q_fd, qinv_fd;
+  double      ninv_fd[2], ninv_w1_fd[2];
+  const void *fwd_fd;
+  const void *inv_fd;
+  const void *fwd_ct_fd;
+  const void *inv_ct_fd;
   /* inverse last stage: N^-1 and N^-1 * w_inv[1] as multipliers */
   ntt_cuda_mulc_t ninv;
   ntt_cuda_mulc_t ninv_w1;
@@ -56,6 +66,8 @@ typedef struct ntt_cuda_params {
 } ntt_cuda_params_t;
 
 const char *ntt_cuda_error(void);
+/* kernel selection for benchmarks / A-B tests: key "ring" or "fp64", value 0/1 */
+int         ntt_cuda_configure(const char *key, int value);
 int         ntt_cuda_device_count(void);
 
 int ntt_cuda_malloc(int device, void **d_ptr, size_t bytes);
@@ -78,6 +90,10 @@ int ntt_cuda_build_tables(int device, const ntt_cuda_params_t *p, const uint64_t
 /* Re-lay the last four stages of (wu, qq) into the [15][N/16] pass-C tables (N >= 16). */
 int ntt_cuda_build_ctables(int device, const ntt_cuda_params_t *p, const void *d_wu, const void *d_qq, void *d_ct_wu,
                            void *d_ct_qq, void *stream);
+/* FP64 twiddles: d_fd[i] = (w[i], RN(w[i]/q)) from the reference-format table d_w; d_ct_fd (may be NULL) =
+ * the last four stages in the [15][N/16] pass-C layout. */
+int ntt_cuda_build_fd_tables(int device, const ntt_cuda_params_t *p, const uint64_t *d_w, void *d_fd, void *d_ct_fd,
+                             void *stream);
 /* Generate the reference-format table d_w[bitrev(i)] = root^i mod q on the device. */
 int ntt_cuda_gen_root_table(int device, uint64_t *d_w, uint64_t root, uint64_t N, uint64_t q, void *stream);
 

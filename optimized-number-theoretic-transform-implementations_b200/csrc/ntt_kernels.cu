@@ -30,6 +30,7 @@
 #include "ntt_cuda.h"
 #include "ntt_device.cuh"
 #include "ntt_ring.cuh"
+#include "ntt_ring_fp.cuh"
 
 using namespace nttb200;
 
@@ -292,9 +293,10 @@ __global__ void __launch_bounds__(ChunkCfg<L>::THREADS, ChunkCfg<L>::MINB) k_chu
  * Global stages s0 .. s0+R-1 of every polynomial (forward order; the inverse runs them backwards).
  * Thread <-> group g of a polynomial: es = N >> (s0+R), block i = g / es, offset j = g % es, coefficients
  * at i*(es<<R) + j + k*es.  Consecutive threads have consecutive j, so each of the 2^R loads/stores of a
- * warp covers 256 contiguous bytes.  FINISH applies the final reduction (inverse pass ending at stage 0).
+ * warp covers 256 contiguous bytes.
  */
-template <int R, bool FWD, bool EXACT, bool FINISH>
+/* OUT: 0 = leave lazy, 1 = final reduction to [0,q), 2 = bring below 2q (what the FP64 chunk kernel accepts) */
+template <int R, bool FWD, bool EXACT, int OUT>
 __global__ void __launch_bounds__(256) k_strided(const __grid_constant__ ntt_cuda_params_t p,
                                                  uint64_t *__restrict__ a, uint32_t s0, size_t total_groups)
 {
@@ -314,7 +316,15 @@ __global__ void __launch_bounds__(256) k_strided(const __grid_constant__ ntt_cud
     for(int k = 0; k < n; k++) x[k] = base[(size_t)k << es_log];
     radix_network<R, FWD, EXACT>(x, p, s0, i);
 #pragma unroll
-    for(int k = 0; k < n; k++) base[(size_t)k << es_log] = FINISH ? finish<EXACT>(x[k], p) : x[k];
+    for(int k = 0; k < n; k++) {
+      uint64_t v = x[k];
+      if(OUT == 1) v = finish<EXACT>(v, p);
+      if(OUT == 2 && !EXACT) {
+        const Red rc{p.q, p.negq, p.red_shift, p.red_mu};
+        v = reduce_2q(v, rc);
+      }
+      base[(size_t)k << es_log] = v;
+    }
   }
 }
 
@@ -506,6 +516,42 @@ extern "C" int ntt_cuda_build_tables(int device, const ntt_cuda_params_t *p, con
   return 0;
 }
 
+/* ---- FP64 twiddles ----------------------------------------------------------------------------------- */
+
+__global__ void k_build_fd(const uint64_t *__restrict__ d_w, double2 *__restrict__ fd, double2 *__restrict__ ct,
+                           uint32_t logn, uint64_t q)
+{
+  const size_t n  = (size_t)1 << logn;
+  const double qd = (double)q;
+  for(size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double w = (double)(d_w[i] % q); /* exact: q < 2^49 */
+    fd[i]          = make_double2(w, __ddiv_rn(w, qd));
+  }
+  if(ct) {
+    const size_t G = n >> 4;
+    for(size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < 15 * G; i += (size_t)gridDim.x * blockDim.x) {
+      const uint32_t t = (uint32_t)(i / G);
+      const size_t   g = i % G;
+      const uint32_t u = 31u - __clz(t + 1u), sub = t + 1u - (1u << u);
+      const double   w = (double)(d_w[((size_t)1 << (logn - 4 + u)) + (g << u) + sub] % q);
+      ct[i]            = make_double2(w, __ddiv_rn(w, qd));
+    }
+  }
+}
+
+extern "C" int ntt_cuda_build_fd_tables(int device, const ntt_cuda_params_t *p, const uint64_t *d_w, void *d_fd,
+                                        void *d_ct_fd, void *stream)
+{
+  DevGuard g(device);
+  if(!g.ok) return fail_msg("cudaSetDevice failed");
+  if(d_ct_fd && p->logn < 4) return fail_msg("pass-C tables need N >= 16");
+  const size_t n      = (size_t)1 << p->logn;
+  const int    blocks = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
+  k_build_fd<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_w, (double2 *)d_fd, (double2 *)d_ct_fd, p->logn, p->q);
+  CU(cudaGetLastError());
+  return 0;
+}
+
 /* ---- pass-C tables ---------------------------------------------------------------------------------- */
 
 /* ct[t*G + g] = entry 2^(logn-4+u) + g*2^u + sub of the stage tables, t = 2^u-1+sub, G = N/16 */
@@ -576,21 +622,42 @@ static int make_block_tmap(CUtensorMap *tm, uint64_t *d_a, size_t total_words)
   return 0;
 }
 
+/* kernel-selection switches (benchmarks and A/B parity tests): environment at first use, or ntt_cuda_configure */
+static int g_ring_on = -1, g_fp64_on = -1;
 static bool ring_enabled()
 {
-  static int on = -1;
-  if(on < 0) {
+  if(g_ring_on < 0) {
     const char *e = getenv("NTT_B200_NO_RING");
-    on            = (e && e[0] == '1') ? 0 : 1;
+    g_ring_on     = (e && e[0] == '1') ? 0 : 1;
   }
-  return on == 1;
+  return g_ring_on == 1;
+}
+extern "C" int ntt_cuda_configure(const char *key, int value)
+{
+  if(key && !strcmp(key, "ring")) { g_ring_on = value ? 1 : 0; return 0; }
+  if(key && !strcmp(key, "fp64")) { g_fp64_on = value ? 1 : 0; return 0; }
+  return fail_msg("unknown configuration key");
 }
 
-template <int L, bool FWD>
+static bool fp64_enabled()
+{
+  if(g_fp64_on < 0) {
+    const char *e = getenv("NTT_B200_NO_FP64");
+    g_fp64_on     = (e && e[0] == '1') ? 0 : 1;
+  }
+  return g_fp64_on == 1;
+}
+/* does this (plan, direction) run its chunk stage on the FP64 ring kernel? */
+static bool use_fp64(const ntt_cuda_params_t &p, bool fwd)
+{
+  return fp64_enabled() && p.fp64 && (fwd ? p.fwd_ct_fd : p.inv_ct_fd) != nullptr;
+}
+
+template <int L, bool FWD, bool FP>
 static int launch_ring(int device, const ntt_cuda_params_t &p, uint64_t *d_a, size_t n_chunks, cudaStream_t st)
 {
   using C = RingCfg<L>;
-  auto        kern = k_ring<L, FWD>;
+  auto        kern = FP ? k_ring_fp<L, FWD> : k_ring<L, FWD>;
   static bool ready[64] = {false};
   if(!ready[device & 63]) {
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
@@ -615,10 +682,17 @@ static int try_ring(int device, int L, const ntt_cuda_params_t &p, uint64_t *d_a
   if(!(FWD ? p.fwd_ct_wu : p.inv_ct_wu)) return 0;
   if(((uintptr_t)d_a & 127) != 0) return 0; /* TMA wants 128-byte aligned rows (cudaMalloc gives 256) */
   *done = true;
+  if(use_fp64(p, FWD)) {
+    switch(L) {
+      case 12: return launch_ring<12, FWD, true>(device, p, d_a, n_chunks, st);
+      case 13: return launch_ring<13, FWD, true>(device, p, d_a, n_chunks, st);
+      default: return launch_ring<14, FWD, true>(device, p, d_a, n_chunks, st);
+    }
+  }
   switch(L) {
-    case 12: return launch_ring<12, FWD>(device, p, d_a, n_chunks, st);
-    case 13: return launch_ring<13, FWD>(device, p, d_a, n_chunks, st);
-    default: return launch_ring<14, FWD>(device, p, d_a, n_chunks, st);
+    case 12: return launch_ring<12, FWD, false>(device, p, d_a, n_chunks, st);
+    case 13: return launch_ring<13, FWD, false>(device, p, d_a, n_chunks, st);
+    default: return launch_ring<14, FWD, false>(device, p, d_a, n_chunks, st);
   }
 }
 
@@ -659,7 +733,7 @@ static int dispatch_chunk(int device, int L, const ntt_cuda_params_t &p, uint64_
   }
 }
 
-template <int R, bool FWD, bool EXACT, bool FINISH>
+template <int R, bool FWD, bool EXACT, int OUT>
 static int launch_strided(int device, const ntt_cuda_params_t &p, uint64_t *d_a, uint32_t s0, size_t batch,
                           cudaStream_t st)
 {
@@ -667,21 +741,21 @@ static int launch_strided(int device, const ntt_cuda_params_t &p, uint64_t *d_a,
   size_t       grid  = (total + 255) / 256;
   const size_t cap   = (size_t)sm_count(device) * 32;
   if(grid > cap) grid = cap;
-  k_strided<R, FWD, EXACT, FINISH><<<(unsigned)grid, 256, 0, st>>>(p, d_a, s0, total);
+  k_strided<R, FWD, EXACT, OUT><<<(unsigned)grid, 256, 0, st>>>(p, d_a, s0, total);
   CU(cudaGetLastError());
   return 0;
 }
 
-template <bool FWD, bool EXACT, bool FINISH>
+template <bool FWD, bool EXACT, int OUT>
 static int dispatch_strided(int device, int R, const ntt_cuda_params_t &p, uint64_t *d_a, uint32_t s0,
                             size_t batch, cudaStream_t st)
 {
   switch(R) {
-    case 1: return launch_strided<1, FWD, EXACT, FINISH>(device, p, d_a, s0, batch, st);
-    case 2: return launch_strided<2, FWD, EXACT, FINISH>(device, p, d_a, s0, batch, st);
-    case 3: return launch_strided<3, FWD, EXACT, FINISH>(device, p, d_a, s0, batch, st);
-    case 4: return launch_strided<4, FWD, EXACT, FINISH>(device, p, d_a, s0, batch, st);
-    case 5: return launch_strided<5, FWD, EXACT, FINISH>(device, p, d_a, s0, batch, st);
+    case 1: return launch_strided<1, FWD, EXACT, OUT>(device, p, d_a, s0, batch, st);
+    case 2: return launch_strided<2, FWD, EXACT, OUT>(device, p, d_a, s0, batch, st);
+    case 3: return launch_strided<3, FWD, EXACT, OUT>(device, p, d_a, s0, batch, st);
+    case 4: return launch_strided<4, FWD, EXACT, OUT>(device, p, d_a, s0, batch, st);
+    case 5: return launch_strided<5, FWD, EXACT, OUT>(device, p, d_a, s0, batch, st);
     default: return fail_msg("unsupported strided radix");
   }
 }
@@ -760,8 +834,12 @@ static int forward_impl(int device, const ntt_cuda_params_t &p, uint64_t *d_a, s
 {
   const Split sp = make_split((int)p.logn);
   uint32_t    s0 = 0;
+  /* the FP64 chunk kernel wants inputs below 2^52: the last strided pass then hands over values below 2q */
+  const bool fp_next = !EXACT && ring_enabled() && p.lazy && sp.L >= 12 && use_fp64(p, true) && ((uintptr_t)d_a & 127) == 0;
   for(int k = 0; k < sp.ns; k++) {
-    if(dispatch_strided<true, EXACT, false>(device, sp.r[k], p, d_a, s0, batch, st)) return -1;
+    const int rc = (fp_next && k == sp.ns - 1) ? dispatch_strided<true, EXACT, 2>(device, sp.r[k], p, d_a, s0, batch, st)
+                                               : dispatch_strided<true, EXACT, 0>(device, sp.r[k], p, d_a, s0, batch, st);
+    if(rc) return -1;
     s0 += sp.r[k];
   }
   if(!EXACT) {
@@ -784,8 +862,8 @@ static int inverse_impl(int device, const ntt_cuda_params_t &p, uint64_t *d_a, s
   uint32_t s0 = s1;
   for(int k = sp.ns - 1; k >= 0; k--) {
     s0 -= sp.r[k];
-    const int rc = (k == 0) ? dispatch_strided<false, EXACT, true>(device, sp.r[k], p, d_a, s0, batch, st)
-                            : dispatch_strided<false, EXACT, false>(device, sp.r[k], p, d_a, s0, batch, st);
+    const int rc = (k == 0) ? dispatch_strided<false, EXACT, 1>(device, sp.r[k], p, d_a, s0, batch, st)
+                            : dispatch_strided<false, EXACT, 0>(device, sp.r[k], p, d_a, s0, batch, st);
     if(rc) return -1;
   }
   return 0;
@@ -828,3 +906,16 @@ extern "C" int ntt_cuda_pointwise(int device, const ntt_cuda_params_t *p, uint64
   CU(cudaGetLastError());
   return 0;
 }
+
+#ifdef NTT_FP_DEBUG
+extern "C" int ntt_cuda_fp_debug(double *out8, unsigned int *count)
+{
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out8, nttb200::g_fp_dbg, 8 * sizeof(double));
+  cudaMemcpyFromSymbol(count, nttb200::g_fp_dbg_n, sizeof(unsigned int));
+  unsigned int mx = 0;
+  cudaMemcpyFromSymbol(&mx, nttb200::g_fp_dbg_max, sizeof(unsigned int));
+  out8[7] = mx;
+  return 0;
+}
+#endif

@@ -1,0 +1,352 @@
+/*
+ * csrc/ntt_ring_fp.cuh -- the ring kernel with the butterflies on the FP64 pipe (q < 2^49).
+ *
+ * Why: on B200 the integer butterfly of ntt_device.cuh costs about 32 SM-cycles per warp (five 32x32->64
+ * products dominate), while DFMA/DADD/DMUL issue at 61 lanes/clk/SM.  An exact FP64 formulation needs 8
+ * FP64 instructions per butterfly plus 3 per coefficient per pass, and measures 1.33x the integer rate in the
+ * register-only microbenchmark (tools/ubench_mix.cu, profiles/r01_ubench_mix.txt).  The two do not overlap
+ * (they share issue bandwidth), so the whole network runs in FP64.
+ *
+ * Exactness.  Coefficients are integers held in doubles, signed, |v| < 2^53.  For a twiddle w in [0,q) with
+ * winv = RN(w/q) and any integer y:
+ *     c = rint(y*winv)                      (magic-constant rounding: c is an integer near w*y/q)
+ *     h = RN(w*y),  l = fma(w, y, -h)       (error-free product: w*y = h + l exactly)
+ *     d = fma(-c, q, h)                     (exact: |h - c*q| < 2^53)
+ *     t = d + l                             (exact)  =>  t = w*y - c*q == w*y (mod q), an integer
+ * so the residue is exact whatever c is; rounding only decides how large |t| gets:
+ * |t| <= q*(0.5 + 1.01*|y|/2^52) as long as c really is rint(y*winv).  Butterflies are X' = X + t, Y' = X - t
+ * (forward) and X' = X + Y, Y' = t(X - Y) (inverse) with no range correction; every pass first folds its
+ * inputs to |v| <= q/2 + 6 (v - rint(v/q)*q, 3 instructions).  Forward, 5 stages from a fold: multiplied
+ * operands stay below 3.3q < 2^51 (fp_mul's rounding trick is exact there), values below 4.2q.  Inverse, 4
+ * stages from a fold: sums double to 8q + 96 < 2^52 (q <= 2^49 - 1024), which fp_mul_wide still rounds
+ * exactly; 5-stage inverse passes fold once more after their first three stages.
+ * The last pass folds, adds q to negatives and converts back to u64: the output is the canonical residue in
+ * [0,q), bit-identical to fwd_ntt_ref_harvey / inv_ntt_ref_harvey (include/ntt_reference.h:19-31,
+ * src/ntt_reference.c:33-66).
+ *
+ * Data path, ring, TMA, swizzle, pass structure: identical to ntt_ring.cuh (see there).  Between passes the
+ * slots hold doubles instead of u64.
+ */
+#pragma once
+#include "ntt_ring.cuh"
+
+namespace nttb200 {
+
+struct FpC {
+  double q, qinv, magic;
+};
+#define NTT_FP_MAGIC 6755399441055744.0 /* 1.5 * 2^52 */
+
+/* v - rint(v/q)*q: |result| <= 0.51 q for |v| < 2^53 (q < 2^49) */
+__device__ __forceinline__ double fp_fold(double v, const FpC &c)
+{
+  const double k = __dadd_rn(__fma_rn(v, c.qinv, c.magic), -c.magic);
+  return __fma_rn(-k, c.q, v);
+}
+/* t == w*y (mod q), exact integer, small (see the header) */
+__device__ __forceinline__ double fp_mul(double y, double w, double winv, const FpC &c)
+{
+  const double cc = __dadd_rn(__fma_rn(y, winv, c.magic), -c.magic);
+  const double h  = __dmul_rn(y, w);
+  const double l  = __fma_rn(y, w, -h);
+  const double d  = __fma_rn(-cc, c.q, h);
+  return __dadd_rn(d, l);
+}
+/* Same product for |y| < 2^52 (inverse passes, where X - Y reaches 8q): the magic-constant rounding above is
+ * only an integer for |y*winv| < 2^51 (a negative argument beyond that lands where ulp = 1/2), so round the
+ * magnitude with 2^52 instead -- exact for |arg| < 2^52 -- and put the sign on q: d = h - sign(arg)*c*q.
+ * 7 FP64 instructions + 1 LOP3. */
+__device__ __forceinline__ double fp_mul_wide(double y, double w, double winv, const FpC &c)
+{
+  const double arg = __dmul_rn(y, winv);
+  const double ca  = __dadd_rn(__dadd_rn(fabs(arg), 4503599627370496.0), -4503599627370496.0);
+  const double qs  = __hiloint2double(__double2hiint(c.q) ^ (int)((~(uint32_t)__double2hiint(arg)) & 0x80000000u),
+                                      __double2loint(c.q)); /* -q if arg >= 0, +q if arg < 0 */
+  const double h   = __dmul_rn(y, w);
+  const double l   = __fma_rn(y, w, -h);
+  const double d   = __fma_rn(ca, qs, h);
+  return __dadd_rn(d, l);
+}
+/* u64 below 2^52 -> the same integer as a double (exponent splice + one DADD) */
+__device__ __forceinline__ double fp_from_u64(uint64_t v)
+{
+  return __dadd_rn(__hiloint2double((int)(hi32(v) | 0x43300000u), (int)lo32(v)), -4503599627370496.0);
+}
+/* |v| < q, integer  ->  canonical residue in [0,q) as u64 */
+__device__ __forceinline__ uint64_t fp_to_u64(double v, const FpC &c)
+{
+  const double r = v < 0.0 ? __dadd_rn(v, c.q) : v;
+  const double t = __dadd_rn(r, 4503599627370496.0);
+  return pack64((uint32_t)__double2loint(t), (uint32_t)__double2hiint(t) & 0x000fffffu);
+}
+
+__device__ __forceinline__ void fp_bfly_fwd(double &x, double &y, double2 tw, const FpC &c)
+{
+  const double t = fp_mul(y, tw.x, tw.y, c);
+  y              = __dadd_rn(x, -t);
+  x              = __dadd_rn(x, t);
+}
+__device__ __forceinline__ void fp_bfly_inv(double &x, double &y, double2 tw, const FpC &c)
+{
+  const double d = __dadd_rn(x, -y);
+  x              = __dadd_rn(x, y);
+  y              = fp_mul_wide(d, tw.x, tw.y, c);
+}
+
+/* R-stage network; TWF(t) returns twiddle entry t = 2^u-1+sub of this group.  Inputs are folded first; a
+ * 5-stage inverse network folds again after its first three stages.  FINAL: the inverse network ends with
+ * global stage 0, whose two products carry N^-1 (harvey_bkw_butterfly_final, fast_mul_operators.h:94-106). */
+#ifdef NTT_FP_DEBUG
+__device__ double g_fp_dbg[8];
+__device__ unsigned int g_fp_dbg_n;
+__device__ unsigned int g_fp_dbg_max;
+__device__ __forceinline__ void fp_check(double v, int tag, int u)
+{
+  if(v != floor(v) || fabs(v) > 4.6e15) {
+    if(atomicAdd(&g_fp_dbg_n, 1u) == 0) { g_fp_dbg[0] = v; g_fp_dbg[1] = tag; g_fp_dbg[2] = u; g_fp_dbg[3] = blockIdx.x; g_fp_dbg[4] = threadIdx.x; }
+  }
+}
+#define FP_CHECK(v, tag, u) fp_check(v, tag, u)
+#else
+#define FP_CHECK(v, tag, u)
+#endif
+
+template <int R, bool FWD, bool FINAL, typename TWF>
+__device__ __forceinline__ void fp_network(double (&x)[1 << R], const FpC &c, const ntt_cuda_params_t &p, TWF twf)
+{
+  constexpr int n = 1 << R;
+#pragma unroll
+  for(int k = 0; k < n; k++) { FP_CHECK(x[k], 100 + R, -1); x[k] = fp_fold(x[k], c); FP_CHECK(x[k], 200 + R, -1); }
+  if(FWD) {
+#pragma unroll
+    for(int u = 0; u < R; u++) {
+      const int d = n >> (u + 1);
+#pragma unroll
+      for(int sub = 0; sub < (1 << u); sub++) {
+        const double2 tw = twf((1 << u) - 1 + sub);
+#pragma unroll
+        for(int k = 0; k < d; k++) fp_bfly_fwd(x[sub * 2 * d + k], x[sub * 2 * d + k + d], tw, c);
+      }
+    }
+  } else {
+#pragma unroll
+    for(int u = R - 1; u >= 0; u--) {
+      const int d = n >> (u + 1);
+      if(R == 5 && u == 1) {
+#pragma unroll
+        for(int k = 0; k < n; k++) x[k] = fp_fold(x[k], c);
+      }
+      if(FINAL && u == 0) {
+        const double2 a = make_double2(p.ninv_fd[0], p.ninv_fd[1]), b = make_double2(p.ninv_w1_fd[0], p.ninv_w1_fd[1]);
+#pragma unroll
+        for(int k = 0; k < d; k++) {
+          const double s = __dadd_rn(x[k], x[k + d]), df = __dadd_rn(x[k], -x[k + d]);
+#ifdef NTT_FP_DEBUG
+          atomicMax(&g_fp_dbg_max, (unsigned int)(fmax(fabs(x[k]), fabs(x[k + d])) / c.q * 1000.0));
+#endif
+          x[k]           = fp_mul_wide(s, a.x, a.y, c);
+          x[k + d]       = fp_mul_wide(df, b.x, b.y, c);
+        }
+      } else {
+#pragma unroll
+        for(int sub = 0; sub < (1 << u); sub++) {
+          const double2 tw = twf((1 << u) - 1 + sub);
+#pragma unroll
+          for(int k = 0; k < d; k++) {
+            fp_bfly_inv(x[sub * 2 * d + k], x[sub * 2 * d + k + d], tw, c);
+            FP_CHECK(x[sub * 2 * d + k], 300 + R, u);
+            FP_CHECK(x[sub * 2 * d + k + d], 400 + R, u);
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int L, bool FWD>
+__global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
+  k_ring_fp(const __grid_constant__ ntt_cuda_params_t p, const __grid_constant__ CUtensorMap tmap, size_t n_chunks)
+{
+  using C = RingCfg<L>;
+  constexpr int NB = C::NB, RA = C::RA, SLOTS = C::SLOTS, T = C::THREADS, HALF = NB / 2;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t ring     = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t *      ring_ptr = smem_raw + (ring - smem_u32(smem_raw));
+  double2 *      tw_s     = reinterpret_cast<double2 *>(ring_ptr + SLOTS * 4096); /* NTW x 16 bytes */
+  const uint32_t bars     = ring + SLOTS * 4096 + C::TW_BYTES;
+
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t s1        = p.logn - L;
+  const size_t   my_polys  = (n_chunks > blockIdx.x) ? (n_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const size_t   my_blocks = my_polys * NB;
+  const size_t   groups    = (size_t)1 << (p.logn - 4);
+  const FpC      c{p.q_fd, p.qinv_fd, NTT_FP_MAGIC};
+  const double2 *g_fd  = (const double2 *)(FWD ? p.fwd_fd : p.inv_fd);
+  const double2 *g_ct  = (const double2 *)(FWD ? p.fwd_ct_fd : p.inv_ct_fd);
+
+  auto slot_addr  = [&](size_t g) -> uint32_t { return ring + (uint32_t)(g % SLOTS) * 4096u; };
+  auto issue_load = [&](size_t g) {
+    if(g >= my_blocks) return;
+    const size_t   k     = g / NB;
+    const uint32_t b     = (uint32_t)(g % NB);
+    const size_t   chunk = blockIdx.x + k * gridDim.x;
+    const uint32_t bar   = bars + 8u * (uint32_t)(k % C::NBAR);
+    mbar_arrive_expect_tx(bar, 4096u);
+    tma_load_block(slot_addr(g), &tmap, (int)((chunk << (L - 4)) + b * 32u), bar);
+  };
+
+  if(tid == 0) {
+    tma_prefetch_desc(&tmap);
+    for(int i = 0; i < C::NBAR; i++) mbar_init(bars + 8u * i, NB);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  for(uint32_t g = tid; g < (uint32_t)SLOTS; g += T) issue_load(g);
+
+  uint32_t cached_cp = 0xffffffffu;
+  for(size_t k = 0; k < my_polys; k++) {
+    const size_t   chunk = blockIdx.x + k * gridDim.x;
+    const uint32_t cp    = (uint32_t)(chunk & (((size_t)1 << s1) - 1));
+    if(cp != cached_cp) {
+      __syncthreads();
+      for(uint32_t e = tid; e < (uint32_t)C::NTW; e += T) {
+        uint32_t t, st, blk;
+        if(e < (uint32_t)(NB - 1)) {
+          t = e; st = s1; blk = cp;
+        } else {
+          const uint32_t r = e - (NB - 1);
+          t = r % 31u; st = s1 + RA; blk = cp * NB + r / 31u;
+        }
+        const uint32_t u = 31u - __clz(t + 1u), sub = t + 1u - (1u << u);
+        tw_s[e] = __ldg(g_fd + (((size_t)1 << (st + u)) + ((size_t)blk << u) + sub));
+      }
+      cached_cp = cp;
+      __syncthreads();
+    }
+    const size_t   g0  = k * NB;
+    const uint32_t sl0 = (uint32_t)(g0 % SLOTS);
+    mbar_wait(bars + 8u * (uint32_t)(k % C::NBAR), (uint32_t)((k / C::NBAR) & 1));
+
+    auto blk_slot = [&](uint32_t b) -> uint32_t {
+      uint32_t s = sl0 + b;
+      return s >= (uint32_t)SLOTS ? s - SLOTS : s;
+    };
+
+    /* pass A: across blocks.  Forward: first pass, reads the raw u64 input.  Inverse: last pass, writes u64. */
+    auto pass_a = [&]() {
+      for(uint32_t j = tid; j < 512u; j += T) {
+        const uint32_t off = slot_off(j);
+        double         x[NB];
+#pragma unroll
+        for(int b = 0; b < NB; b++) {
+          const uint64_t raw = *reinterpret_cast<const uint64_t *>(ring_ptr + blk_slot(b) * 4096u + off);
+          x[b]               = FWD ? fp_from_u64(raw) : __longlong_as_double((long long)raw);
+        }
+        if(!FWD && s1 == 0) {
+          fp_network<RA, FWD, true>(x, c, p, [&](int t) { return tw_s[t]; });
+        } else {
+          fp_network<RA, FWD, false>(x, c, p, [&](int t) { return tw_s[t]; });
+        }
+#pragma unroll
+        for(int b = 0; b < NB; b++) {
+          uint64_t out;
+          if(FWD) {
+            out = (uint64_t)__double_as_longlong(x[b]);
+          } else {
+            /* inverse: this is the chunk kernel's last pass; with s1 == 0 the values are final products
+             * (|v| < q), otherwise they are folded first; either way the canonical residue goes out */
+            const double v = (s1 == 0) ? x[b] : fp_fold(x[b], c);
+            out            = fp_to_u64(v, c);
+          }
+          *reinterpret_cast<uint64_t *>(ring_ptr + blk_slot(b) * 4096u + off) = out;
+        }
+      }
+    };
+
+    const uint32_t hb = lane >> 4, jb = lane & 15u;
+    const uint32_t blkB = warp + hb * HALF;
+    auto pass_b = [&]() {
+      uint8_t *      base = ring_ptr + blk_slot(blkB) * 4096u + ((jb & 1u) << 3);
+      const uint32_t jc   = jb >> 1;
+      const double2 *tw   = tw_s + (NB - 1) + blkB * 31;
+      double         x[32];
+#pragma unroll
+      for(int kk = 0; kk < 32; kk++)
+        x[kk] = *reinterpret_cast<const double *>(base + kk * 128 + ((jc ^ (uint32_t)(kk & 7)) << 4));
+      fp_network<5, FWD, false>(x, c, p, [&](int t) { return tw[t]; });
+#pragma unroll
+      for(int kk = 0; kk < 32; kk++)
+        *reinterpret_cast<double *>(base + kk * 128 + ((jc ^ (uint32_t)(kk & 7)) << 4)) = x[kk];
+    };
+
+    /* pass C: 16 contiguous coefficients.  Forward: last pass, writes canonical u64.  Inverse: first pass,
+     * reads the raw u64 input (contract [0,2q)). */
+    auto pass_c = [&](uint32_t blk) {
+      uint8_t *base = ring_ptr + blk_slot(blk) * 4096u + lane * 128u;
+      double   x[16];
+#pragma unroll
+      for(int cc = 0; cc < 8; cc++) {
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(base + (((uint32_t)cc ^ (lane & 7u)) << 4));
+        x[2 * cc]     = FWD ? __longlong_as_double((long long)v.x) : fp_from_u64(v.x);
+        x[2 * cc + 1] = FWD ? __longlong_as_double((long long)v.y) : fp_from_u64(v.y);
+      }
+      const double2 *tw = g_ct + ((size_t)cp * NB + blk) * 32 + lane;
+      fp_network<4, FWD, false>(x, c, p, [&](int t) { return __ldg(tw + (size_t)t * groups); });
+#pragma unroll
+      for(int cc = 0; cc < 8; cc++) {
+        ulonglong2 v;
+        if(FWD) {
+          v.x = fp_to_u64(fp_fold(x[2 * cc], c), c);
+          v.y = fp_to_u64(fp_fold(x[2 * cc + 1], c), c);
+        } else {
+          v.x = (uint64_t)__double_as_longlong(x[2 * cc]);
+          v.y = (uint64_t)__double_as_longlong(x[2 * cc + 1]);
+        }
+        *reinterpret_cast<ulonglong2 *>(base + (((uint32_t)cc ^ (lane & 7u)) << 4)) = v;
+      }
+    };
+
+    auto store_block = [&](uint32_t b) {
+      tma_store_block(&tmap, (int)((chunk << (L - 4)) + b * 32u), ring + blk_slot(b) * 4096u);
+      tma_commit();
+    };
+
+    if(FWD) {
+      pass_a();
+      __syncthreads();
+      pass_b();
+      __syncwarp();
+      pass_c(warp);
+      fence_proxy_async();
+      __syncwarp();
+      if(lane == 0) store_block(warp);
+      pass_c(warp + HALF);
+      fence_proxy_async();
+      __syncwarp();
+      if(lane == 0) {
+        store_block(warp + HALF);
+        tma_wait_read_all();
+        issue_load(g0 + warp + SLOTS);
+        issue_load(g0 + warp + HALF + SLOTS);
+      }
+      __syncwarp();
+    } else {
+      pass_c(warp);
+      pass_c(warp + HALF);
+      __syncwarp();
+      pass_b();
+      __syncthreads();
+      pass_a();
+      fence_proxy_async();
+      __syncthreads();
+      if(tid < (uint32_t)NB) {
+        store_block(tid);
+        tma_wait_read_all();
+        issue_load(g0 + tid + SLOTS);
+      }
+    }
+  }
+  tma_wait_all();
+}
+
+}  // namespace nttb200

@@ -18,6 +18,7 @@
 typedef unsigned __int128 u128;
 
 #define LAZY_MAX_QBITS 56 /* lazy path needs (4 + 10*24) * q < 2^64 */
+#define FP64_MAX_QBITS 49 /* FP64 path: bounds of csrc/ntt_ring_fp.cuh hold for q <= 2^49 - 1024 */
 #define HOST_PIPE_DEPTH 3
 #define HOST_PIPE_BYTES ((size_t)32 << 20)
 
@@ -31,6 +32,7 @@ struct ntt_b200_plan {
   /* device memory: kernel tables and the reference-format copies kept for export */
   void *    d_fwd_wu, *d_fwd_qq, *d_inv_wu, *d_inv_qq;
   void *    d_fwd_ct_wu, *d_fwd_ct_qq, *d_inv_ct_wu, *d_inv_ct_qq; /* pass-C layout of the last four stages */
+  void *    d_fwd_fd, *d_inv_fd, *d_fwd_ct_fd, *d_inv_ct_fd;         /* FP64 path twiddles (q < 2^49) */
   uint64_t *d_w, *d_w_con, *d_w_inv, *d_w_inv_con;
   /* host-buffer pipeline (created on first use) */
   pthread_mutex_t pipe_lock;
@@ -55,6 +57,12 @@ static int cuda_error(const char *where)
 const char *ntt_b200_last_error(void) { return g_error; }
 int         ntt_b200_device_count(void) { return ntt_cuda_device_count(); }
 const char *ntt_b200_version(void) { return "ntt_b200 0.1 sm_100a"; }
+
+int ntt_b200_configure(const char *key, int value)
+{
+  if(ntt_cuda_configure(key, value)) return cuda_error("configure");
+  return NTT_B200_SUCCESS;
+}
 
 /* ---- multiplier constants ------------------------------------------------------------------------ */
 
@@ -102,6 +110,10 @@ static void fill_params(ntt_b200_plan_t *pl)
   p->lazy      = nttm_bitlen(pl->q) <= LAZY_MAX_QBITS ? 1u : 0u;
   p->red_shift = nttm_bitlen(pl->q) > 9 ? nttm_bitlen(pl->q) - 9 : 0;
   p->red_mu    = (uint32_t)((((u128)1) << (32 + p->red_shift)) / pl->q);
+  /* FP64 ring kernel: q < 2^49 and a chunk size the ring kernel serves */
+  p->fp64    = (pl->q <= ((uint64_t)1 << FP64_MAX_QBITS) - 1024 && pl->logn >= 12) ? 1u : 0u;
+  p->q_fd    = (double)pl->q;
+  p->qinv_fd = 1.0 / (double)pl->q;
 }
 
 static void plan_free(ntt_b200_plan_t *pl)
@@ -109,7 +121,7 @@ static void plan_free(ntt_b200_plan_t *pl)
   if(!pl) return;
   void *dev_ptrs[] = {pl->d_fwd_wu,    pl->d_fwd_qq,    pl->d_inv_wu,    pl->d_inv_qq, pl->d_w,    pl->d_w_con,
                       pl->d_w_inv,     pl->d_w_inv_con, pl->d_fwd_ct_wu, pl->d_fwd_ct_qq, pl->d_inv_ct_wu,
-                      pl->d_inv_ct_qq};
+                      pl->d_inv_ct_qq, pl->d_fwd_fd,    pl->d_inv_fd,    pl->d_fwd_ct_fd, pl->d_inv_ct_fd};
   for(size_t i = 0; i < sizeof(dev_ptrs) / sizeof(dev_ptrs[0]); i++) {
     if(dev_ptrs[i]) ntt_cuda_free(pl->device, dev_ptrs[i]);
   }
@@ -157,8 +169,23 @@ static int build_ctables(ntt_b200_plan_t *pl, const void *wu, const void *qq, vo
   return NTT_B200_SUCCESS;
 }
 
+/* FP64 twiddles of one direction (only for plans the FP64 kernel can serve) */
+static int build_fd(ntt_b200_plan_t *pl, const uint64_t *d_w, void **fd, void **ct_fd)
+{
+  if(!pl->params.fp64) return NTT_B200_SUCCESS;
+  const size_t n = (size_t)pl->N;
+  if(ntt_cuda_malloc(pl->device, fd, n * 16) || ntt_cuda_malloc(pl->device, ct_fd, (size_t)15 * (n / 16) * 16))
+    return cuda_error("table alloc");
+  if(ntt_cuda_build_fd_tables(pl->device, &pl->params, d_w, *fd, *ct_fd, NULL)) return cuda_error("table build");
+  return NTT_B200_SUCCESS;
+}
+
 static void publish_tables(ntt_b200_plan_t *pl)
 {
+  pl->params.fwd_fd    = pl->d_fwd_fd;
+  pl->params.inv_fd    = pl->d_inv_fd;
+  pl->params.fwd_ct_fd = pl->d_fwd_ct_fd;
+  pl->params.inv_ct_fd = pl->d_inv_ct_fd;
   pl->params.fwd_wu    = pl->d_fwd_wu;
   pl->params.fwd_qq    = pl->d_fwd_qq;
   pl->params.inv_wu    = pl->d_inv_wu;
@@ -174,6 +201,14 @@ static int finish_inverse_constants(ntt_b200_plan_t *pl, uint64_t w_inv_1)
   const int lazy      = (int)pl->params.lazy;
   pl->params.ninv     = make_mulc(pl->n_inv, pl->q, lazy);
   pl->params.ninv_w1  = make_mulc(nttm_mulmod(pl->n_inv % pl->q, w_inv_1 % pl->q, pl->q), pl->q, lazy);
+  {
+    const double qd = (double)pl->q;
+    const double a = (double)(pl->n_inv % pl->q), b = (double)nttm_mulmod(pl->n_inv % pl->q, w_inv_1 % pl->q, pl->q);
+    pl->params.ninv_fd[0]    = a;
+    pl->params.ninv_fd[1]    = a / qd;
+    pl->params.ninv_w1_fd[0] = b;
+    pl->params.ninv_w1_fd[1] = b / qd;
+  }
   if(lazy && ntt_cuda_plan_inverse_bounds(&pl->params)) return cuda_error("inverse bounds");
   return NTT_B200_SUCCESS;
 }
@@ -188,6 +223,8 @@ static int adopt_table(ntt_b200_plan_t *pl, const uint64_t *w, const uint64_t *w
   int rc = build_direction(pl, *d_w, wu, qq, d_con);
   if(!rc) rc = (wu == &pl->d_fwd_wu) ? build_ctables(pl, *wu, *qq, &pl->d_fwd_ct_wu, &pl->d_fwd_ct_qq)
                                      : build_ctables(pl, *wu, *qq, &pl->d_inv_ct_wu, &pl->d_inv_ct_qq);
+  if(!rc) rc = (wu == &pl->d_fwd_wu) ? build_fd(pl, *d_w, &pl->d_fwd_fd, &pl->d_fwd_ct_fd)
+                                     : build_fd(pl, *d_w, &pl->d_inv_fd, &pl->d_inv_ct_fd);
   if(rc) return rc;
   if(w_con) {
     uint64_t *chk = malloc(bytes);
@@ -272,6 +309,8 @@ int ntt_b200_plan_create_psi(ntt_b200_plan_t **plan, int device, uint64_t N, uin
   if(!rc) rc = build_direction(pl, pl->d_w_inv, &pl->d_inv_wu, &pl->d_inv_qq, &pl->d_w_inv_con);
   if(!rc) rc = build_ctables(pl, pl->d_fwd_wu, pl->d_fwd_qq, &pl->d_fwd_ct_wu, &pl->d_fwd_ct_qq);
   if(!rc) rc = build_ctables(pl, pl->d_inv_wu, pl->d_inv_qq, &pl->d_inv_ct_wu, &pl->d_inv_ct_qq);
+  if(!rc) rc = build_fd(pl, pl->d_w, &pl->d_fwd_fd, &pl->d_fwd_ct_fd);
+  if(!rc) rc = build_fd(pl, pl->d_w_inv, &pl->d_inv_fd, &pl->d_inv_ct_fd);
   if(!rc && ntt_cuda_sync(device, NULL)) rc = cuda_error("table generation");
   /* w_inv[1] = psi_inv^(N/2) */
   if(!rc) rc = finish_inverse_constants(pl, nttm_powmod(psi_inv, N / 2, q));

@@ -220,6 +220,36 @@ def test_headline_config_roundtrip_and_linearity(ntt, oracle, golden_synth):
     plan.close()
 
 
+def test_kernel_paths_agree_on_full_batch(ntt, oracle, golden_synth):
+    """The three CUDA paths (FP64 ring, integer ring, generic smem kernel) must produce identical bytes on a
+    large batch, forward and inverse, on inputs at the edge of the contracts; rows are spot-checked vs the oracle."""
+    s = [x for x in golden_synth if x["m"] == 14][0]
+    N, q, batch = 1 << 14, s["q"], 2048
+    t = CaseTables(oracle, 14, q, s["psi"], s["psi_inv"], s["n_inv"])
+    plan = ntt.Plan.from_psi(N, q, s["psi"])
+    a4 = oracle.uniform(batch * N, 4 * q, 51).reshape(batch, N)   # forward contract [0,4q)
+    a2 = oracle.uniform(batch * N, 2 * q, 52).reshape(batch, N)   # inverse contract [0,2q)
+    outs = {}
+    try:
+        for name, ring, fp in (("fp64", 1, 1), ("int", 1, 0), ("generic", 0, 0)):
+            ntt.configure("ring", ring)
+            ntt.configure("fp64", fp)
+            df, di = to_dev(a4), to_dev(a2)
+            plan.fwd(df, batch)
+            plan.inv(di, batch)
+            outs[name] = (to_host(df), to_host(di))
+    finally:
+        ntt.configure("ring", 1)
+        ntt.configure("fp64", 1)
+    for name in ("int", "generic"):
+        assert np.array_equal(outs["fp64"][0], outs[name][0]), "forward: fp64 vs %s" % name
+        assert np.array_equal(outs["fp64"][1], outs[name][1]), "inverse: fp64 vs %s" % name
+    for r in (0, 151, 206, 1023, 2047):
+        assert np.array_equal(outs["fp64"][0][r], oracle.fwd(a4[r], q, t.w, t.w_con))
+        assert np.array_equal(outs["fp64"][1][r], oracle.inv(a2[r], q, t.n_inv, t.w_inv, t.w_inv_con))
+    plan.close()
+
+
 def test_rns_limbs(ntt, oracle):
     """BASELINE config 3 shape (scaled down): N=2^16, several ~50-bit limbs, each with its own q."""
     N, m, limbs, per = 1 << 16, 16, 3, 2
