@@ -907,15 +907,12 @@ extern "C" int ntt_cuda_pointwise(int device, const ntt_cuda_params_t *p, uint64
   return 0;
 }
 
-#ifdef NTT_FP_DEBUG
-extern "C" int ntt_cuda_fp_debug(double *out8, unsigned int *count)
+
+#ifdef NTT_RING_TRACE
+extern "C" int ntt_cuda_trace_read(long long *out, size_t n)
 {
   cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(out8, nttb200::g_fp_dbg, 8 * sizeof(double));
-  cudaMemcpyFromSymbol(count, nttb200::g_fp_dbg_n, sizeof(unsigned int));
-  unsigned int mx = 0;
-  cudaMemcpyFromSymbol(&mx, nttb200::g_fp_dbg_max, sizeof(unsigned int));
-  out8[7] = mx;
+  cudaMemcpyFromSymbol(out, nttb200::g_trace, n * sizeof(long long));
   return 0;
 }
 #endif

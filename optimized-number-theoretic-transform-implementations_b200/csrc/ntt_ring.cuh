@@ -92,6 +92,11 @@ __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commi
 __device__ __forceinline__ void tma_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 /* ... and have finished writing global memory */
 __device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+/* pull one 4-KiB block into L2 ahead of its (later) TMA load */
+__device__ __forceinline__ void tma_prefetch_block_l2(const CUtensorMap *tm, int row)
+{
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tm), "r"(0), "r"(row) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *tm)
 {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");

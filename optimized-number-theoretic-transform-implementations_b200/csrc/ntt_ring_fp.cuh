@@ -86,37 +86,24 @@ __device__ __forceinline__ void fp_bfly_fwd(double &x, double &y, double2 tw, co
   y              = __dadd_rn(x, -t);
   x              = __dadd_rn(x, t);
 }
+/* WIDE: the difference may exceed 2^51 (fourth stage after a fold), use the rounding that is exact up to 2^52 */
+template <bool WIDE>
 __device__ __forceinline__ void fp_bfly_inv(double &x, double &y, double2 tw, const FpC &c)
 {
   const double d = __dadd_rn(x, -y);
   x              = __dadd_rn(x, y);
-  y              = fp_mul_wide(d, tw.x, tw.y, c);
+  y              = WIDE ? fp_mul_wide(d, tw.x, tw.y, c) : fp_mul(d, tw.x, tw.y, c);
 }
 
 /* R-stage network; TWF(t) returns twiddle entry t = 2^u-1+sub of this group.  Inputs are folded first; a
  * 5-stage inverse network folds again after its first three stages.  FINAL: the inverse network ends with
  * global stage 0, whose two products carry N^-1 (harvey_bkw_butterfly_final, fast_mul_operators.h:94-106). */
-#ifdef NTT_FP_DEBUG
-__device__ double g_fp_dbg[8];
-__device__ unsigned int g_fp_dbg_n;
-__device__ unsigned int g_fp_dbg_max;
-__device__ __forceinline__ void fp_check(double v, int tag, int u)
-{
-  if(v != floor(v) || fabs(v) > 4.6e15) {
-    if(atomicAdd(&g_fp_dbg_n, 1u) == 0) { g_fp_dbg[0] = v; g_fp_dbg[1] = tag; g_fp_dbg[2] = u; g_fp_dbg[3] = blockIdx.x; g_fp_dbg[4] = threadIdx.x; }
-  }
-}
-#define FP_CHECK(v, tag, u) fp_check(v, tag, u)
-#else
-#define FP_CHECK(v, tag, u)
-#endif
-
 template <int R, bool FWD, bool FINAL, typename TWF>
 __device__ __forceinline__ void fp_network(double (&x)[1 << R], const FpC &c, const ntt_cuda_params_t &p, TWF twf)
 {
   constexpr int n = 1 << R;
 #pragma unroll
-  for(int k = 0; k < n; k++) { FP_CHECK(x[k], 100 + R, -1); x[k] = fp_fold(x[k], c); FP_CHECK(x[k], 200 + R, -1); }
+  for(int k = 0; k < n; k++) x[k] = fp_fold(x[k], c);
   if(FWD) {
 #pragma unroll
     for(int u = 0; u < R; u++) {
@@ -141,9 +128,6 @@ __device__ __forceinline__ void fp_network(double (&x)[1 << R], const FpC &c, co
 #pragma unroll
         for(int k = 0; k < d; k++) {
           const double s = __dadd_rn(x[k], x[k + d]), df = __dadd_rn(x[k], -x[k + d]);
-#ifdef NTT_FP_DEBUG
-          atomicMax(&g_fp_dbg_max, (unsigned int)(fmax(fabs(x[k]), fabs(x[k + d])) / c.q * 1000.0));
-#endif
           x[k]           = fp_mul_wide(s, a.x, a.y, c);
           x[k + d]       = fp_mul_wide(df, b.x, b.y, c);
         }
@@ -153,15 +137,24 @@ __device__ __forceinline__ void fp_network(double (&x)[1 << R], const FpC &c, co
           const double2 tw = twf((1 << u) - 1 + sub);
 #pragma unroll
           for(int k = 0; k < d; k++) {
-            fp_bfly_inv(x[sub * 2 * d + k], x[sub * 2 * d + k + d], tw, c);
-            FP_CHECK(x[sub * 2 * d + k], 300 + R, u);
-            FP_CHECK(x[sub * 2 * d + k + d], 400 + R, u);
+            /* stages since the last fold: R = 4 reaches its fourth at u == 0 (|X - Y| up to 8q) */
+            if(R == 4 && u == 0) fp_bfly_inv<true>(x[sub * 2 * d + k], x[sub * 2 * d + k + d], tw, c);
+            else fp_bfly_inv<false>(x[sub * 2 * d + k], x[sub * 2 * d + k + d], tw, c);
           }
         }
       }
     }
   }
 }
+
+/* -DNTT_RING_TRACE: CTA 0 records clock64() at the phase boundaries of its first 64 polynomials (read back with
+ * ntt_cuda_trace_read); how the per-pass cycle counts in DESIGN.md were obtained. */
+#ifdef NTT_RING_TRACE
+__device__ long long g_trace[16 * 64 * 8]; /* [warp][poly][event] for CTA 0 */
+#define TRACE(ev) do { if(blockIdx.x == 0 && lane == 0 && k < 64) g_trace[(warp * 64 + k) * 8 + (ev)] = clock64(); } while(0)
+#else
+#define TRACE(ev)
+#endif
 
 template <int L, bool FWD>
 __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
@@ -225,7 +218,18 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
     }
     const size_t   g0  = k * NB;
     const uint32_t sl0 = (uint32_t)(g0 % SLOTS);
+    /* blocks g0+SLOTS .. g0+SLOTS+NB-1 get their slot only when this polynomial's blocks are stored; ask L2
+     * for them now so that the late TMA loads find them on chip */
+    if(tid < (uint32_t)NB) {
+      const size_t g = g0 + SLOTS + tid;
+      if(g < my_blocks) {
+        const size_t ck = blockIdx.x + (g / NB) * gridDim.x;
+        tma_prefetch_block_l2(&tmap, (int)((ck << (L - 4)) + (uint32_t)(g % NB) * 32u));
+      }
+    }
+    TRACE(0);
     mbar_wait(bars + 8u * (uint32_t)(k % C::NBAR), (uint32_t)((k / C::NBAR) & 1));
+    TRACE(1);
 
     auto blk_slot = [&](uint32_t b) -> uint32_t {
       uint32_t s = sl0 + b;
@@ -281,7 +285,7 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
 
     /* pass C: 16 contiguous coefficients.  Forward: last pass, writes canonical u64.  Inverse: first pass,
      * reads the raw u64 input (contract [0,2q)). */
-    auto pass_c = [&](uint32_t blk) {
+    auto pass_c = [&](uint32_t blk, bool rearm_first) {
       uint8_t *base = ring_ptr + blk_slot(blk) * 4096u + lane * 128u;
       double   x[16];
 #pragma unroll
@@ -289,6 +293,11 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
         const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(base + (((uint32_t)cc ^ (lane & 7u)) << 4));
         x[2 * cc]     = FWD ? __longlong_as_double((long long)v.x) : fp_from_u64(v.x);
         x[2 * cc + 1] = FWD ? __longlong_as_double((long long)v.y) : fp_from_u64(v.y);
+      }
+      if(FWD && rearm_first && lane == 0) {
+        /* the first block's store has had this block's shared-memory loads to drain: re-arm its slot now */
+        tma_wait_read_all();
+        issue_load(g0 + warp + SLOTS);
       }
       const double2 *tw = g_ct + ((size_t)cp * NB + blk) * 32 + lane;
       fp_network<4, FWD, false>(x, c, p, [&](int t) { return __ldg(tw + (size_t)t * groups); });
@@ -313,26 +322,31 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
 
     if(FWD) {
       pass_a();
+      TRACE(2);
       __syncthreads();
+      TRACE(3);
       pass_b();
       __syncwarp();
-      pass_c(warp);
+      TRACE(4);
+      pass_c(warp, false);
       fence_proxy_async();
       __syncwarp();
       if(lane == 0) store_block(warp);
-      pass_c(warp + HALF);
+      TRACE(5);
+      pass_c(warp + HALF, true);
       fence_proxy_async();
       __syncwarp();
+      TRACE(6);
       if(lane == 0) {
         store_block(warp + HALF);
         tma_wait_read_all();
-        issue_load(g0 + warp + SLOTS);
         issue_load(g0 + warp + HALF + SLOTS);
       }
       __syncwarp();
+      TRACE(7);
     } else {
-      pass_c(warp);
-      pass_c(warp + HALF);
+      pass_c(warp, false);
+      pass_c(warp + HALF, false);
       __syncwarp();
       pass_b();
       __syncthreads();
