@@ -657,17 +657,26 @@ template <int L, bool FWD, bool FP>
 static int launch_ring(int device, const ntt_cuda_params_t &p, uint64_t *d_a, size_t n_chunks, cudaStream_t st)
 {
   using C = RingCfg<L>;
-  auto        kern = FP ? k_ring_fp<L, FWD> : k_ring<L, FWD>;
+  auto        kern = k_ring<L, FWD>;
+  auto        kern_fp = k_ring_fp<L, FWD>;
   static bool ready[64] = {false};
   if(!ready[device & 63]) {
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    if(FP) {
+      CU(cudaFuncSetAttribute(kern_fp, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    } else {
+      CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    }
     ready[device & 63] = true;
   }
   CUtensorMap tm;
   if(make_block_tmap(&tm, d_a, n_chunks << L)) return -1;
   size_t grid = (size_t)sm_count(device) * C::CTAS;
   if(grid > n_chunks) grid = n_chunks;
-  kern<<<(unsigned)grid, C::THREADS, C::SMEM, st>>>(p, tm, n_chunks);
+  if(FP) {
+    kern_fp<<<(unsigned)grid, C::THREADS, C::SMEM, st>>>(p, tm, n_chunks, d_a);
+  } else {
+    kern<<<(unsigned)grid, C::THREADS, C::SMEM, st>>>(p, tm, n_chunks);
+  }
   CU(cudaGetLastError());
   return 0;
 }

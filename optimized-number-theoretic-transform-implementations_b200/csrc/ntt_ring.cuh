@@ -120,7 +120,7 @@ struct RingCfg {
   static constexpr int PER_CTA  = 233472 / CTAS - 1024;
   static constexpr int BUDGET   = PER_CTA < 232448 ? PER_CTA : 232448;
   static constexpr int SLOTS    = (BUDGET - TW_BYTES - 1024 - 64) / 4096;  /* 50 / 24 / 12 for L = 14 / 13 / 12 */
-  static constexpr int SMEM     = SLOTS * 4096 + 1024 /* alignment slack */ + TW_BYTES + 64 /* barriers */;
+  static constexpr int SMEM     = SLOTS * 4096 + 1024 /* alignment slack */ + TW_BYTES + 64 /* 8 barriers */;
   static_assert(SLOTS > NB && 4 * NB > SLOTS, "ring depth vs. mbarrier reuse distance");
 };
 
@@ -414,10 +414,13 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
       pass_a();
       fence_proxy_async();
       __syncthreads();
-      if(tid < (uint32_t)NB) {
-        store_block(tid);
+      /* every warp drains and re-arms its own two blocks (one warp doing all NB stores serialises ~4 us) */
+      if(lane == 0) {
+        store_block(warp);
+        store_block(warp + HALF);
         tma_wait_read_all();
-        issue_load(g0 + tid + SLOTS);
+        issue_load(g0 + warp + SLOTS);
+        issue_load(g0 + warp + HALF + SLOTS);
       }
     }
   }

@@ -158,7 +158,8 @@ __device__ long long g_trace[16 * 64 * 8]; /* [warp][poly][event] for CTA 0 */
 
 template <int L, bool FWD>
 __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
-  k_ring_fp(const __grid_constant__ ntt_cuda_params_t p, const __grid_constant__ CUtensorMap tmap, size_t n_chunks)
+  k_ring_fp(const __grid_constant__ ntt_cuda_params_t p, const __grid_constant__ CUtensorMap tmap, size_t n_chunks,
+            uint64_t *__restrict__ p_out)
 {
   using C = RingCfg<L>;
   constexpr int NB = C::NB, RA = C::RA, SLOTS = C::SLOTS, T = C::THREADS, HALF = NB / 2;
@@ -183,19 +184,21 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
     const size_t   k     = g / NB;
     const uint32_t b     = (uint32_t)(g % NB);
     const size_t   chunk = blockIdx.x + k * gridDim.x;
-    const uint32_t bar   = bars + 8u * (uint32_t)(k % C::NBAR);
+    /* two barriers per polynomial in flight: blocks [0,HALF) and [HALF,NB).  The low half always sits in slots
+     * that were free long ago; the high half may have been re-armed only when the previous polynomial was
+     * stored, so the inverse starts on the low half while the rest is still landing. */
+    const uint32_t bar = bars + 8u * (2u * (uint32_t)(k % C::NBAR) + (b >= (uint32_t)HALF ? 1u : 0u));
     mbar_arrive_expect_tx(bar, 4096u);
     tma_load_block(slot_addr(g), &tmap, (int)((chunk << (L - 4)) + b * 32u), bar);
   };
 
   if(tid == 0) {
     tma_prefetch_desc(&tmap);
-    for(int i = 0; i < C::NBAR; i++) mbar_init(bars + 8u * i, NB);
+    for(int i = 0; i < 2 * C::NBAR; i++) mbar_init(bars + 8u * i, HALF);
     fence_barrier_init();
   }
   __syncthreads();
   for(uint32_t g = tid; g < (uint32_t)SLOTS; g += T) issue_load(g);
-
   uint32_t cached_cp = 0xffffffffu;
   for(size_t k = 0; k < my_polys; k++) {
     const size_t   chunk = blockIdx.x + k * gridDim.x;
@@ -228,7 +231,10 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
       }
     }
     TRACE(0);
-    mbar_wait(bars + 8u * (uint32_t)(k % C::NBAR), (uint32_t)((k / C::NBAR) & 1));
+    const uint32_t bar_lo = bars + 16u * (uint32_t)(k % C::NBAR), bar_hi = bar_lo + 8u;
+    const uint32_t parity = (uint32_t)((k / C::NBAR) & 1);
+    mbar_wait(bar_lo, parity);
+    if(FWD) mbar_wait(bar_hi, parity);
     TRACE(1);
 
     auto blk_slot = [&](uint32_t b) -> uint32_t {
@@ -236,33 +242,54 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
       return s >= (uint32_t)SLOTS ? s - SLOTS : s;
     };
 
-    /* pass A: across blocks.  Forward: first pass, reads the raw u64 input.  Inverse: last pass, writes u64. */
-    auto pass_a = [&]() {
+    /* pass A, forward: first pass; reads the raw u64 input from the slots, leaves doubles in place. */
+    auto pass_a_fwd = [&]() {
       for(uint32_t j = tid; j < 512u; j += T) {
         const uint32_t off = slot_off(j);
         double         x[NB];
 #pragma unroll
-        for(int b = 0; b < NB; b++) {
-          const uint64_t raw = *reinterpret_cast<const uint64_t *>(ring_ptr + blk_slot(b) * 4096u + off);
-          x[b]               = FWD ? fp_from_u64(raw) : __longlong_as_double((long long)raw);
-        }
-        if(!FWD && s1 == 0) {
-          fp_network<RA, FWD, true>(x, c, p, [&](int t) { return tw_s[t]; });
+        for(int b = 0; b < NB; b++)
+          x[b] = fp_from_u64(*reinterpret_cast<const uint64_t *>(ring_ptr + blk_slot(b) * 4096u + off));
+        fp_network<RA, true, false>(x, c, p, [&](int t) { return tw_s[t]; });
+#pragma unroll
+        for(int b = 0; b < NB; b++)
+          *reinterpret_cast<double *>(ring_ptr + blk_slot(b) * 4096u + off) = x[b];
+      }
+    };
+    /* pass A, inverse: last pass.  Every thread first pulls its column(s) into registers; after one
+     * __syncthreads the polynomial's slots are dead and are re-armed at once (the next polynomials' blocks get
+     * a whole pass of lead time), and the results go from registers straight to global memory: column j of
+     * block b is word b*512+j, so a warp writes 256 contiguous bytes per store instruction.  No TMA store,
+     * no proxy fence, no drain wait on this side. */
+    auto pass_a_inv = [&]() {
+      constexpr int COLS = 512 / T; /* columns per thread: 1 at L = 14 */
+      double        x[COLS][NB];
+#pragma unroll
+      for(int cidx = 0; cidx < COLS; cidx++) {
+        const uint32_t off = slot_off(tid + cidx * T);
+#pragma unroll
+        for(int b = 0; b < NB; b++) x[cidx][b] = *reinterpret_cast<const double *>(ring_ptr + blk_slot(b) * 4096u + off);
+      }
+      __syncthreads();
+      if(lane == 0) {
+        issue_load(g0 + warp + SLOTS);
+        issue_load(g0 + warp + HALF + SLOTS);
+      }
+      uint64_t *gout = p_out + (chunk << L);
+#pragma unroll
+      for(int cidx = 0; cidx < COLS; cidx++) {
+        if(s1 == 0) {
+          fp_network<RA, false, true>(x[cidx], c, p, [&](int t) { return tw_s[t]; });
         } else {
-          fp_network<RA, FWD, false>(x, c, p, [&](int t) { return tw_s[t]; });
+          fp_network<RA, false, false>(x[cidx], c, p, [&](int t) { return tw_s[t]; });
         }
+        const uint32_t j = tid + cidx * T;
 #pragma unroll
         for(int b = 0; b < NB; b++) {
-          uint64_t out;
-          if(FWD) {
-            out = (uint64_t)__double_as_longlong(x[b]);
-          } else {
-            /* inverse: this is the chunk kernel's last pass; with s1 == 0 the values are final products
-             * (|v| < q), otherwise they are folded first; either way the canonical residue goes out */
-            const double v = (s1 == 0) ? x[b] : fp_fold(x[b], c);
-            out            = fp_to_u64(v, c);
-          }
-          *reinterpret_cast<uint64_t *>(ring_ptr + blk_slot(b) * 4096u + off) = out;
+          /* with s1 == 0 the values are final products (|v| < q); otherwise fold first.  Either way the
+           * canonical residue goes out (the strided inverse passes that follow accept [0,2q)). */
+          const double v = (s1 == 0) ? x[cidx][b] : fp_fold(x[cidx][b], c);
+          gout[(size_t)b * 512 + j] = fp_to_u64(v, c);
         }
       }
     };
@@ -321,7 +348,7 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
     };
 
     if(FWD) {
-      pass_a();
+      pass_a_fwd();
       TRACE(2);
       __syncthreads();
       TRACE(3);
@@ -346,18 +373,18 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
       TRACE(7);
     } else {
       pass_c(warp, false);
+      TRACE(2);
+      mbar_wait(bar_hi, parity);
       pass_c(warp + HALF, false);
       __syncwarp();
+      TRACE(3);
       pass_b();
+      TRACE(4);
       __syncthreads();
-      pass_a();
-      fence_proxy_async();
-      __syncthreads();
-      if(tid < (uint32_t)NB) {
-        store_block(tid);
-        tma_wait_read_all();
-        issue_load(g0 + tid + SLOTS);
-      }
+      TRACE(5);
+      pass_a_inv();
+      TRACE(6);
+      TRACE(7);
     }
   }
   tma_wait_all();
