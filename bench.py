@@ -108,7 +108,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.02)
+            self._stop.wait(0.002)
 
     def start(self):
         if self.nv is not None:
@@ -243,14 +243,16 @@ def load_peak():
 
 
 def load_compute_bound(fwd_ntt_per_s):
-    """The integer-pipe roofline of the butterfly (register-only microbenchmark tools/ubench_bfly.cu, result
-    committed in profiles/traffic.json): north_star's roofline is the slower of HBM and this."""
+    """The arithmetic-pipe roofline of the forward kernel: measured DFMA issue rate (tools/ubench_pipes.cu) divided
+    by the FP64 instructions one transform executes; north_star's roofline is the slower of HBM and this.
+    (The integer formulation's bound, from tools/ubench_bfly.cu, is reported beside it.)"""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
             t = json.load(fh)
-        peak = float(t["int_pipe_bfly_per_s"]) / float(t["bfly_per_fwd_ntt_logn14"])
-        return {"bound": "integer pipe (IMAD)", "peak_ntt_per_s": peak, "achieved_ntt_per_s": fwd_ntt_per_s,
-                "frac": fwd_ntt_per_s / peak, "source": t.get("int_pipe_source")}
+        peak = float(t["fp64_ops_per_s"]) / float(t["fp64_ops_per_fwd_ntt_logn14"])
+        return {"bound": "FP64 pipe (DFMA/DADD/DMUL issue rate)", "peak_ntt_per_s": peak,
+                "achieved_ntt_per_s": fwd_ntt_per_s, "frac": fwd_ntt_per_s / peak, "source": t.get("fp64_source"),
+                "integer_path_peak_ntt_per_s": float(t["int_pipe_bfly_per_s"]) / float(t["bfly_per_fwd_ntt_logn14"])}
     except Exception:
         return None
 
@@ -353,7 +355,7 @@ def run_b200_arm(args):
     achieved = alg_bytes / (fwd_ms * 1e-3) / 1e9
     traffic = load_traffic(args.logn)
     roofline = {
-        "bound": "hbm", "kernel": "k_ring<%d,fwd> (one launch = %d transforms)" % (args.logn, batch),
+        "bound": "hbm", "kernel": "k_ring_fp<%d,fwd> (one launch = %d transforms)" % (args.logn, batch),
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": None if traffic is None else traffic * batch, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": fwd_ms,

@@ -13,6 +13,6 @@ kill $SMI
 python bench.py --impl reference --steps 5 --warmup 1 | tee $OUT/${TAG}_bench_reference.json
 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file $OUT/${TAG}_launches.csv \
     python bench.py --steps 3 --warmup 3 --batch 1024 --no-cpu-baseline > $OUT/${TAG}_ncu_launch_run.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_chunk -s 6 -c 2 -f -o $OUT/${TAG}_prof \
+ncu --set full --clock-control none --import-source on -k regex:'k_ring|k_chunk' -s 6 -c 2 -f -o $OUT/${TAG}_prof \
     python bench.py --steps 2 --warmup 3 --batch 1024 --no-cpu-baseline > $OUT/${TAG}_ncu_full_run.log 2>&1
 ls -la $OUT | tail -12
