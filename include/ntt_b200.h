@@ -129,6 +129,30 @@ int ntt_b200_negacyclic_mul_batch(const ntt_b200_plan_t *plan, uint64_t *d_c, ui
 int ntt_b200_pointwise_mul_batch(const ntt_b200_plan_t *plan, uint64_t *d_c, const uint64_t *d_a,
                                  const uint64_t *d_b, size_t batch, void *stream);
 
+/* ---- one transform spread over several GPUs (SURVEY.md section 8e, N = 2^22 config) ----------------------- */
+
+/*
+ * Building blocks of the distributed transform over G = 2^log2_parts devices.  With the input held CYCLICALLY
+ * (device p owns a[p + G*k]) the first log2(N/G) stages of src/ntt_reference.c:19-30 are exactly a complete
+ * forward NTT of size N/G with root psi^G on each slice (use an ordinary plan for (N/G, q, psi^G) and
+ * ntt_b200_fwd_batch); after one all-to-all to CONTIGUOUS blocks (device r owns a[r*N/G .. (r+1)*N/G)), the
+ * last log2_parts stages are local again:
+ *   ntt_b200_fwd_tail_block  runs them on block `block` (N/G words at d_block) with the size-N plan's tables and
+ *                            fully reduces: the blocks then hold fwd_ntt_ref_harvey's output, in order.
+ *   ntt_b200_inv_tail_block  the mirror image: the first log2_parts stages of inv_ntt_ref_harvey
+ *                            (src/ntt_reference.c:43-53) on a contiguous block, output below 2q; exchange back to
+ *                            cyclic slices and finish with the size-N/G inverse whose scale was set to N^-1.
+ * The exchange itself is the caller's (NCCL all-to-all; see optimized-..._b200/fourstep.py).
+ */
+int ntt_b200_fwd_tail_block(const ntt_b200_plan_t *plan, uint64_t *d_block, uint32_t log2_parts, uint32_t block,
+                            void *stream);
+int ntt_b200_inv_tail_block(const ntt_b200_plan_t *plan, uint64_t *d_block, uint32_t log2_parts, uint32_t block,
+                            void *stream);
+/* Replace the inverse transform's scaling constant N^-1 by `scale` (mod q): inv_batch then returns
+ * scale * N * (true inverse).  Used by the distributed inverse, whose local size-N/G transform must scale by
+ * the global N^-1. */
+int ntt_b200_plan_set_inverse_scale(ntt_b200_plan_t *plan, uint64_t scale);
+
 /* ---- batched transforms, HOST-resident data (end-to-end path) ---------------------------------------- */
 
 /*

@@ -55,6 +55,9 @@ def _bind():
         getattr(L, f).argtypes = [vp, vp, sz, vp]
     for f in ("ntt_b200_fwd_rns", "ntt_b200_inv_rns"):
         getattr(L, f).argtypes = [C.POINTER(vp), sz, vp, sz, vp]
+    for f in ("ntt_b200_fwd_tail_block", "ntt_b200_inv_tail_block"):
+        getattr(L, f).argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp]
+    L.ntt_b200_plan_set_inverse_scale.argtypes = [vp, u64]
     L.ntt_b200_negacyclic_mul_batch.argtypes = [vp, vp, vp, vp, sz, vp]
     L.ntt_b200_pointwise_mul_batch.argtypes = [vp, vp, vp, vp, sz, vp]
     for f in ("ntt_b200_fwd_batch_host", "ntt_b200_inv_batch_host"):
@@ -95,6 +98,7 @@ EXPORTS = [
     "ntt_b200_plan_export_tables",
     "ntt_b200_fwd_batch", "ntt_b200_fwd_lazy_batch", "ntt_b200_inv_batch",
     "ntt_b200_fwd_rns", "ntt_b200_inv_rns",
+    "ntt_b200_fwd_tail_block", "ntt_b200_inv_tail_block", "ntt_b200_plan_set_inverse_scale",
     "ntt_b200_negacyclic_mul_batch", "ntt_b200_pointwise_mul_batch",
     "ntt_b200_fwd_batch_host", "ntt_b200_inv_batch_host",
     "ntt_b200_host_alloc", "ntt_b200_host_free", "ntt_b200_device_alloc", "ntt_b200_device_free",
@@ -246,6 +250,18 @@ class Plan:
     def pointwise_mul(self, d_c, d_a, d_b, batch, stream=None):
         _check(lib.ntt_b200_pointwise_mul_batch(self._h, _ptr(d_c), _ptr(d_a), _ptr(d_b), batch,
                                                 _stream_ptr(stream)), "pointwise_mul_batch")
+
+    # pieces of a transform spread over 2^log2_parts GPUs (see fourstep.py)
+    def fwd_tail_block(self, d_block, log2_parts, block, stream=None):
+        _check(lib.ntt_b200_fwd_tail_block(self._h, _ptr(d_block), log2_parts, block, _stream_ptr(stream)),
+               "fwd_tail_block")
+
+    def inv_tail_block(self, d_block, log2_parts, block, stream=None):
+        _check(lib.ntt_b200_inv_tail_block(self._h, _ptr(d_block), log2_parts, block, _stream_ptr(stream)),
+               "inv_tail_block")
+
+    def set_inverse_scale(self, scale):
+        _check(lib.ntt_b200_plan_set_inverse_scale(self._h, scale), "plan_set_inverse_scale")
 
     # host-resident data: numpy uint64 array or pinned torch tensor, transformed in place
     def fwd_host(self, h_a, batch):

@@ -100,6 +100,9 @@ int ntt_cuda_gen_root_table(int device, uint64_t *d_w, uint64_t root, uint64_t N
 /* Transforms over `batch` contiguous polynomials of N = 2^logn words at d_a (in place). */
 int ntt_cuda_forward(int device, const ntt_cuda_params_t *p, uint64_t *d_a, size_t batch, void *stream);
 int ntt_cuda_inverse(int device, const ntt_cuda_params_t *p, uint64_t *d_a, size_t batch, void *stream);
+/* last `glog` stages on contiguous block `block` of a transform spread over 2^glog devices (see ntt_kernels.cu) */
+int ntt_cuda_tail(int device, const ntt_cuda_params_t *p, uint64_t *d_block, uint32_t glog, uint32_t block, int inverse,
+                  void *stream);
 /* c = a .* b mod q over n words; inputs < q (any q < 2^62). */
 int ntt_cuda_pointwise(int device, const ntt_cuda_params_t *p, uint64_t *d_c, const uint64_t *d_a,
                        const uint64_t *d_b, size_t n, void *stream);

@@ -298,13 +298,16 @@ __global__ void __launch_bounds__(ChunkCfg<L>::THREADS, ChunkCfg<L>::MINB) k_chu
 /* OUT: 0 = leave lazy, 1 = final reduction to [0,q), 2 = bring below 2q (what the FP64 chunk kernel accepts) */
 template <int R, bool FWD, bool EXACT, int OUT>
 __global__ void __launch_bounds__(256) k_strided(const __grid_constant__ ntt_cuda_params_t p,
-                                                 uint64_t *__restrict__ a, uint32_t s0, size_t total_groups)
+                                                 uint64_t *__restrict__ a, uint32_t s0, size_t first_group,
+                                                 size_t n_groups)
 {
+  /* groups [first_group, first_group + n_groups) of the array that starts at `a`; a multi-GPU tail pass hands
+   * in a virtual base so that only the groups of its own block are touched */
   constexpr int  n      = 1 << R;
   const uint32_t logn   = p.logn;
   const uint32_t es_log = logn - s0 - R;
   const uint32_t gl     = logn - R; /* log2 groups per polynomial */
-  for(size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total_groups;
+  for(size_t t = first_group + (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < first_group + n_groups;
       t += (size_t)gridDim.x * blockDim.x) {
     const size_t   poly = t >> gl;
     const uint32_t g    = (uint32_t)(t & ((1u << gl) - 1u));
@@ -743,30 +746,36 @@ static int dispatch_chunk(int device, int L, const ntt_cuda_params_t &p, uint64_
 }
 
 template <int R, bool FWD, bool EXACT, int OUT>
-static int launch_strided(int device, const ntt_cuda_params_t &p, uint64_t *d_a, uint32_t s0, size_t batch,
-                          cudaStream_t st)
+static int launch_strided(int device, const ntt_cuda_params_t &p, uint64_t *d_a, uint32_t s0, size_t first_group,
+                          size_t n_groups, cudaStream_t st)
 {
-  const size_t total = batch << (p.logn - R);
-  size_t       grid  = (total + 255) / 256;
-  const size_t cap   = (size_t)sm_count(device) * 32;
+  size_t       grid = (n_groups + 255) / 256;
+  const size_t cap  = (size_t)sm_count(device) * 32;
   if(grid > cap) grid = cap;
-  k_strided<R, FWD, EXACT, OUT><<<(unsigned)grid, 256, 0, st>>>(p, d_a, s0, total);
+  k_strided<R, FWD, EXACT, OUT><<<(unsigned)grid, 256, 0, st>>>(p, d_a, s0, first_group, n_groups);
   CU(cudaGetLastError());
   return 0;
 }
 
 template <bool FWD, bool EXACT, int OUT>
-static int dispatch_strided(int device, int R, const ntt_cuda_params_t &p, uint64_t *d_a, uint32_t s0,
-                            size_t batch, cudaStream_t st)
+static int dispatch_strided_groups(int device, int R, const ntt_cuda_params_t &p, uint64_t *d_a, uint32_t s0,
+                                   size_t first_group, size_t n_groups, cudaStream_t st)
 {
   switch(R) {
-    case 1: return launch_strided<1, FWD, EXACT, OUT>(device, p, d_a, s0, batch, st);
-    case 2: return launch_strided<2, FWD, EXACT, OUT>(device, p, d_a, s0, batch, st);
-    case 3: return launch_strided<3, FWD, EXACT, OUT>(device, p, d_a, s0, batch, st);
-    case 4: return launch_strided<4, FWD, EXACT, OUT>(device, p, d_a, s0, batch, st);
-    case 5: return launch_strided<5, FWD, EXACT, OUT>(device, p, d_a, s0, batch, st);
+    case 1: return launch_strided<1, FWD, EXACT, OUT>(device, p, d_a, s0, first_group, n_groups, st);
+    case 2: return launch_strided<2, FWD, EXACT, OUT>(device, p, d_a, s0, first_group, n_groups, st);
+    case 3: return launch_strided<3, FWD, EXACT, OUT>(device, p, d_a, s0, first_group, n_groups, st);
+    case 4: return launch_strided<4, FWD, EXACT, OUT>(device, p, d_a, s0, first_group, n_groups, st);
+    case 5: return launch_strided<5, FWD, EXACT, OUT>(device, p, d_a, s0, first_group, n_groups, st);
     default: return fail_msg("unsupported strided radix");
   }
+}
+
+template <bool FWD, bool EXACT, int OUT>
+static int dispatch_strided(int device, int R, const ntt_cuda_params_t &p, uint64_t *d_a, uint32_t s0, size_t batch,
+                            cudaStream_t st)
+{
+  return dispatch_strided_groups<FWD, EXACT, OUT>(device, R, p, d_a, s0, 0, batch << (p.logn - R), st);
 }
 
 /* How the stages of a 2^logn transform are split: `ns` strided passes of radix 2^r[i] cover the first
@@ -896,6 +905,31 @@ extern "C" int ntt_cuda_inverse(int device, const ntt_cuda_params_t *p, uint64_t
   if(p->logn < 1 || p->logn > NTT_MAX_STAGES) return fail_msg("logn out of range");
   return p->lazy ? inverse_impl<false>(device, *p, d_a, batch, (cudaStream_t)stream)
                  : inverse_impl<true>(device, *p, d_a, batch, (cudaStream_t)stream);
+}
+
+/*
+ * Tail pass of a transform of size N = 2^logn spread over 2^glog devices: the last glog
+ * stages (distances 2^(glog-1) .. 1) on the contiguous block `block` (N >> glog words at d_block).  Forward:
+ * input in [0,4q), output fully reduced.  Inverse: the same stages backwards (they come first), input in
+ * [0,2q), output below 2q for the complete local inverse that follows the exchange.
+ */
+extern "C" int ntt_cuda_tail(int device, const ntt_cuda_params_t *p, uint64_t *d_block, uint32_t glog, uint32_t block,
+                             int inverse, void *stream)
+{
+  DevGuard g(device);
+  if(!g.ok) return fail_msg("cudaSetDevice failed");
+  if(glog < 1 || glog > 5 || 2 * glog > p->logn || block >= (1u << glog)) return fail_msg("bad tail geometry");
+  const uint32_t s0       = p->logn - glog;
+  const size_t   n_groups = (size_t)1 << (p->logn - 2 * glog);       /* groups of 2^glog words in one block */
+  const size_t   first    = (size_t)block * n_groups;
+  uint64_t *     vbase    = d_block - ((size_t)block << (p->logn - glog)); /* virtual start of the polynomial */
+  cudaStream_t   st       = (cudaStream_t)stream;
+  if(p->lazy) {
+    return inverse ? dispatch_strided_groups<false, false, 2>(device, (int)glog, *p, vbase, s0, first, n_groups, st)
+                   : dispatch_strided_groups<true, false, 1>(device, (int)glog, *p, vbase, s0, first, n_groups, st);
+  }
+  return inverse ? dispatch_strided_groups<false, true, 0>(device, (int)glog, *p, vbase, s0, first, n_groups, st)
+                 : dispatch_strided_groups<true, true, 1>(device, (int)glog, *p, vbase, s0, first, n_groups, st);
 }
 
 extern "C" int ntt_cuda_pointwise(int device, const ntt_cuda_params_t *p, uint64_t *d_c, const uint64_t *d_a,

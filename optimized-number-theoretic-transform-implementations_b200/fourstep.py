@@ -1,0 +1,142 @@
+"""One negacyclic NTT of size N spread over G = 2^g GPUs (BASELINE config 5: N = 2^22, one exchange step).
+
+Decomposition (restating the loop nest of src/ntt_reference.c:19-30): with the
+coefficients held CYCLICALLY -- rank p owns a[p + G*k] -- every stage whose butterfly distance is >= G touches
+one residue class only, and on rank p's slice those log2(N/G) stages are exactly a complete forward NTT of size
+N/G with root psi^G (same twiddles for every p).  After ONE all-to-all that re-lays the array out in CONTIGUOUS
+blocks -- rank r owns a[r*N/G .. (r+1)*N/G) -- the remaining g stages (distances G/2 .. 1) are local again and
+finish the transform: rank r then holds words [r*N/G, (r+1)*N/G) of fwd_ntt_ref_harvey's output (bit-reversed
+order, fully reduced).  The inverse is the mirror image: tail stages on contiguous blocks, all-to-all back to
+cyclic slices, complete size-N/G inverse whose scale is the global N^-1.
+
+The local transforms run on the same sm_100a kernels as the batched path (C-ABI: ntt_b200_fwd_batch,
+ntt_b200_fwd_tail_block, ...); torch.distributed (NCCL over NVLink) provides the all-to-all.  One process per GPU.
+"""
+import importlib
+
+import numpy as np
+
+_pkg = importlib.import_module(__name__.rsplit(".", 1)[0])
+
+
+def exchange_cyclic_to_blocks(local, world, dist=None, group=None):
+    """local: this rank's cyclic slice (N/G words, 1-D torch int64 tensor).  Returns this rank's contiguous block.
+
+    Rank p's slice index k holds position e = p + G*k.  Block r needs k in [r*N/G^2, (r+1)*N/G^2) from every p,
+    and position e sits at block offset p + G*(k - r*N/G^2): the received [G, N/G^2] pieces are interleaved.
+    """
+    import torch
+    G = world
+    n_local = local.numel()
+    assert n_local % G == 0
+    piece = n_local // G
+    if G == 1:
+        return local.clone()
+    recv = torch.empty_like(local)
+    if dist.get_backend(group) == "nccl":
+        dist.all_to_all_single(recv, local.contiguous(), group=group)
+    else:  # gloo (CPU tests): all_gather and pick this rank's piece from every source
+        rank = dist.get_rank(group)
+        gathered = [torch.empty_like(local) for _ in range(G)]
+        dist.all_gather(gathered, local.contiguous(), group=group)
+        recv = torch.cat([g[rank * piece:(rank + 1) * piece] for g in gathered])
+    # recv[p*piece + kk] = a[p + G*(r*piece + kk)]  ->  block[kk*G + p]
+    return recv.view(G, piece).t().contiguous().view(-1)
+
+
+def exchange_blocks_to_cyclic(block, world, dist=None, group=None):
+    """Inverse of exchange_cyclic_to_blocks."""
+    import torch
+    G = world
+    n_local = block.numel()
+    piece = n_local // G
+    if G == 1:
+        return block.clone()
+    send = block.view(piece, G).t().contiguous().view(-1)  # send[p*piece + kk] = block[kk*G + p] -> rank p
+    recv = torch.empty_like(send)
+    if dist.get_backend(group) == "nccl":
+        dist.all_to_all_single(recv, send, group=group)
+    else:
+        rank = dist.get_rank(group)
+        gathered = [torch.empty_like(send) for _ in range(G)]
+        dist.all_gather(gathered, send, group=group)
+        recv = torch.cat([g[rank * piece:(rank + 1) * piece] for g in gathered])
+    # from source r: kk-th word is slice index r*piece + kk
+    return recv
+
+
+class DistributedNtt:
+    """Plans of one rank for a size-N transform over `world` = 2^g ranks."""
+
+    def __init__(self, N, q, psi, rank, world, device=0):
+        assert world & (world - 1) == 0 and world >= 1
+        self.N, self.q, self.psi, self.rank, self.world = N, q, psi, rank, world
+        self.g = world.bit_length() - 1
+        assert (N // world) >= world, "need N >= G^2"
+        self.n_local = N // world
+        # complete transforms of the cyclic slices: size N/G, root psi^G
+        self.local = _pkg.Plan.from_psi(self.n_local, q, _pkg.pow_mod(psi, world, q), device=device)
+        # the local inverse must scale by the GLOBAL N^-1 (= (N/G)^-1 * G^-1)
+        self.local.set_inverse_scale(_pkg.pow_mod((q + 1) // 2, N.bit_length() - 1, q))
+        # tail stages use the tables of the full-size transform
+        self.full = _pkg.Plan.from_psi(N, q, psi, device=device) if world > 1 else None
+
+    def forward(self, slice_dev, dist=None, group=None, stream=None):
+        """slice_dev: this rank's cyclic slice a[rank + G*k] on the GPU (modified).  Returns this rank's block of
+        the transform (words [rank*N/G, (rank+1)*N/G) of the reference output)."""
+        self.local.fwd(slice_dev, 1, stream)
+        if self.world == 1:
+            return slice_dev
+        block = exchange_cyclic_to_blocks(slice_dev, self.world, dist, group)
+        self.full.fwd_tail_block(block, self.g, self.rank, stream)
+        return block
+
+    def inverse(self, block_dev, dist=None, group=None, stream=None):
+        """block_dev: this rank's contiguous block of the NTT-domain array.  Returns its cyclic slice of the
+        coefficient array, scaled by N^-1 and fully reduced (inv_ntt_ref_harvey semantics)."""
+        if self.world == 1:
+            self.local.inv(block_dev, 1, stream)
+            return block_dev
+        self.full.inv_tail_block(block_dev, self.g, self.rank, stream)
+        sl = exchange_blocks_to_cyclic(block_dev, self.world, dist, group)
+        self.local.inv(sl, 1, stream)
+        return sl
+
+    def close(self):
+        self.local.close()
+        if self.full is not None:
+            self.full.close()
+
+
+def emulate_forward_single_gpu(N, q, psi, a_host, world):
+    """All `world` ranks emulated one after the other on ONE GPU (no collective): the same kernels and the same
+    index arithmetic as the multi-process path; used by the single-GPU parity test."""
+    import torch
+    G = world
+    parts = [DistributedNtt(N, q, psi, r, G) for r in range(G)]
+    slices = [torch.from_numpy(np.ascontiguousarray(a_host[p::G]).view(np.int64)).cuda() for p in range(G)]
+    for p in range(G):
+        parts[p].local.fwd(slices[p], 1)
+    piece = (N // G) // G
+    out = []
+    for r in range(G):
+        recv = torch.cat([slices[p][r * piece:(r + 1) * piece] for p in range(G)])
+        block = recv.view(G, piece).t().contiguous().view(-1)
+        if G > 1:
+            parts[r].full.fwd_tail_block(block, parts[r].g, r)
+        out.append(block)
+    res = torch.cat(out).cpu().numpy().view(np.uint64)
+    # and back again
+    blocks = [o.clone() for o in out]
+    for r in range(G):
+        if G > 1:
+            parts[r].full.inv_tail_block(blocks[r], parts[r].g, r)
+    sends = [b.view(piece, G).t().contiguous().view(-1) for b in blocks]
+    back = np.empty(N, dtype=np.uint64)
+    for p in range(G):
+        sl = torch.cat([sends[r][p * piece:(p + 1) * piece] for r in range(G)])
+        parts[p].local.inv(sl, 1)
+        back[p::G] = sl.cpu().numpy().view(np.uint64)
+    for d in parts:
+        d.close()
+    return res, back

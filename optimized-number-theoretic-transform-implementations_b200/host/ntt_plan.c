@@ -28,6 +28,7 @@ struct ntt_b200_plan {
   unsigned logn;
   int      has_fwd, has_inv;
   uint64_t n_inv, n_inv_con;
+  uint64_t w_inv_1; /* w_inv[1] = psi^-(N/2), kept to rebuild the stage-0 constants */
   ntt_cuda_params_t params;
   /* device memory: kernel tables and the reference-format copies kept for export */
   void *    d_fwd_wu, *d_fwd_qq, *d_inv_wu, *d_inv_qq;
@@ -198,6 +199,7 @@ static void publish_tables(ntt_b200_plan_t *pl)
 
 static int finish_inverse_constants(ntt_b200_plan_t *pl, uint64_t w_inv_1)
 {
+  pl->w_inv_1 = w_inv_1 % pl->q;
   const int lazy      = (int)pl->params.lazy;
   pl->params.ninv     = make_mulc(pl->n_inv, pl->q, lazy);
   pl->params.ninv_w1  = make_mulc(nttm_mulmod(pl->n_inv % pl->q, w_inv_1 % pl->q, pl->q), pl->q, lazy);
@@ -364,6 +366,30 @@ static int check_batch(const ntt_b200_plan_t *plan, const void *d_a, int need_in
   if(((uintptr_t)d_a & 15) != 0) return set_error("device data must be 16-byte aligned%s", NULL);
   if(need_inv ? !plan->has_inv : !plan->has_fwd)
     return set_error("plan was created without the %s tables", need_inv ? "inverse" : "forward");
+  return NTT_B200_SUCCESS;
+}
+
+int ntt_b200_plan_set_inverse_scale(ntt_b200_plan_t *plan, uint64_t scale)
+{
+  if(!plan || !plan->has_inv) return set_error("plan has no inverse tables%s", NULL);
+  plan->n_inv     = scale % plan->q;
+  plan->n_inv_con = nttm_shoup(plan->n_inv, plan->q, 64);
+  return finish_inverse_constants(plan, plan->w_inv_1);
+}
+
+int ntt_b200_fwd_tail_block(const ntt_b200_plan_t *plan, uint64_t *d_block, uint32_t log2_parts, uint32_t block,
+                            void *stream)
+{
+  if(check_batch(plan, d_block, 0)) return NTT_B200_ERROR;
+  if(ntt_cuda_tail(plan->device, &plan->params, d_block, log2_parts, block, 0, stream)) return cuda_error("forward tail");
+  return NTT_B200_SUCCESS;
+}
+
+int ntt_b200_inv_tail_block(const ntt_b200_plan_t *plan, uint64_t *d_block, uint32_t log2_parts, uint32_t block,
+                            void *stream)
+{
+  if(check_batch(plan, d_block, 1)) return NTT_B200_ERROR;
+  if(ntt_cuda_tail(plan->device, &plan->params, d_block, log2_parts, block, 1, stream)) return cuda_error("inverse tail");
   return NTT_B200_SUCCESS;
 }
 

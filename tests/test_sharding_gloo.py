@@ -62,3 +62,29 @@ def test_shard_range_properties():
                            for l in range(0, total, max(1, total // 5)))
     with pytest.raises(ValueError):
         sh.shard_range(10, 2, 2)
+
+
+# ---- the exchange step of the distributed transform (BASELINE config 5), on CPU tensors over gloo -------------
+
+def _exchange_worker(rank, world, port, n, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    fs = importlib.import_module(PKG + ".fourstep")
+    a = torch.arange(n, dtype=torch.int64) * 7 + 3          # a[e] = 7e + 3: position is recoverable
+    cyclic = a[rank::world].clone()
+    block = fs.exchange_cyclic_to_blocks(cyclic, world, dist)
+    back = fs.exchange_blocks_to_cyclic(block, world, dist)
+    n_local = n // world
+    out[rank] = dict(block_ok=bool(torch.equal(block, a[rank * n_local:(rank + 1) * n_local])),
+                     back_ok=bool(torch.equal(back, cyclic)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [16, 4096])
+def test_world2_cyclic_block_exchange(n):
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_exchange_worker, args=(world, port, n, out), nprocs=world, join=True)
+    assert all(out[r]["block_ok"] and out[r]["back_ok"] for r in range(world))
