@@ -787,6 +787,8 @@ struct Split {
 };
 static Split make_split(int logn)
 {
+  /* as few stages as possible go to the strided passes: measured at N = 2^16, (2 strided + 2^14 chunks) takes
+   * 0.58 ms per 1024 transforms against 0.68 ms for (4 strided + 2^12 chunks) */
   Split s{};
   int   rest = logn > 14 ? logn - 14 : 0; /* stages that do not fit a chunk */
   s.L        = logn - rest;

@@ -72,12 +72,14 @@ __device__ __forceinline__ double fp_from_u64(uint64_t v)
 {
   return __dadd_rn(__hiloint2double((int)(hi32(v) | 0x43300000u), (int)lo32(v)), -4503599627370496.0);
 }
-/* |v| < q, integer  ->  canonical residue in [0,q) as u64 */
-__device__ __forceinline__ uint64_t fp_to_u64(double v, const FpC &c)
+/* |v| < q, integer  ->  canonical residue in [0,q) as u64.  One DADD puts v next to 1.5*2^52, where consecutive
+ * integers are consecutive bit patterns; the rest (subtract the constant's bits, add q to negatives) is integer
+ * work on the otherwise idle ALU pipe. */
+__device__ __forceinline__ uint64_t fp_to_u64(double v, const FpC &c, uint64_t q)
 {
-  const double r = v < 0.0 ? __dadd_rn(v, c.q) : v;
-  const double t = __dadd_rn(r, 4503599627370496.0);
-  return pack64((uint32_t)__double2loint(t), (uint32_t)__double2hiint(t) & 0x000fffffu);
+  const double   t = __dadd_rn(v, c.magic);
+  const long long r = __double_as_longlong(t) - 0x4338000000000000ll; /* = v as a signed integer */
+  return (uint64_t)(r < 0 ? r + (long long)q : r);
 }
 
 __device__ __forceinline__ void fp_bfly_fwd(double &x, double &y, double2 tw, const FpC &c)
@@ -289,7 +291,7 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
           /* with s1 == 0 the values are final products (|v| < q); otherwise fold first.  Either way the
            * canonical residue goes out (the strided inverse passes that follow accept [0,2q)). */
           const double v = (s1 == 0) ? x[cidx][b] : fp_fold(x[cidx][b], c);
-          gout[(size_t)b * 512 + j] = fp_to_u64(v, c);
+          gout[(size_t)b * 512 + j] = fp_to_u64(v, c, p.q);
         }
       }
     };
@@ -332,8 +334,8 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
       for(int cc = 0; cc < 8; cc++) {
         ulonglong2 v;
         if(FWD) {
-          v.x = fp_to_u64(fp_fold(x[2 * cc], c), c);
-          v.y = fp_to_u64(fp_fold(x[2 * cc + 1], c), c);
+          v.x = fp_to_u64(fp_fold(x[2 * cc], c), c, p.q);
+          v.y = fp_to_u64(fp_fold(x[2 * cc + 1], c), c, p.q);
         } else {
           v.x = (uint64_t)__double_as_longlong(x[2 * cc]);
           v.y = (uint64_t)__double_as_longlong(x[2 * cc + 1]);
