@@ -120,8 +120,8 @@ int ntt_b200_inv_rns(ntt_b200_plan_t *const *plans, size_t limbs, uint64_t *d_a,
 
 /*
  * Negacyclic product c = a * b in Z_q[X]/(X^N+1) for `batch` pairs (next row of the scope table:
- * fwd x2, pointwise multiply, inverse).  d_c may alias d_a.  d_a and d_b are overwritten
- * (they hold the forward transforms afterwards when d_c != d_a).
+ * fwd x2, pointwise multiply, inverse).  d_c may alias d_a or d_b.  d_a and d_b are overwritten (work space).
+ * On the FP64 ring kernel the pointwise product is fused into the second forward transform.
  */
 int ntt_b200_negacyclic_mul_batch(const ntt_b200_plan_t *plan, uint64_t *d_c, uint64_t *d_a, uint64_t *d_b,
                                   size_t batch, void *stream);

@@ -76,6 +76,7 @@ int ntt_cuda_host_alloc(void **h_ptr, size_t bytes);
 int ntt_cuda_host_free(void *h_ptr);
 int ntt_cuda_h2d(int device, void *d_dst, const void *h_src, size_t bytes, void *stream);
 int ntt_cuda_d2h(int device, void *h_dst, const void *d_src, size_t bytes, void *stream);
+int ntt_cuda_d2d(int device, void *d_dst, const void *d_src, size_t bytes, void *stream);
 int ntt_cuda_sync(int device, void *stream);
 int ntt_cuda_stream_create(int device, void **stream);
 int ntt_cuda_stream_destroy(int device, void *stream);
@@ -100,6 +101,9 @@ int ntt_cuda_gen_root_table(int device, uint64_t *d_w, uint64_t root, uint64_t N
 /* Transforms over `batch` contiguous polynomials of N = 2^logn words at d_a (in place). */
 int ntt_cuda_forward(int device, const ntt_cuda_params_t *p, uint64_t *d_a, size_t batch, void *stream);
 int ntt_cuda_inverse(int device, const ntt_cuda_params_t *p, uint64_t *d_a, size_t batch, void *stream);
+/* forward transform of d_a followed by d_a .*= d_other; *fused_out says whether the kernel did the product */
+int ntt_cuda_forward_mul(int device, const ntt_cuda_params_t *p, uint64_t *d_a, const uint64_t *d_other, size_t batch,
+                         void *stream, int *fused_out);
 /* last `glog` stages on contiguous block `block` of a transform spread over 2^glog devices (see ntt_kernels.cu) */
 int ntt_cuda_tail(int device, const ntt_cuda_params_t *p, uint64_t *d_block, uint32_t glog, uint32_t block, int inverse,
                   void *stream);

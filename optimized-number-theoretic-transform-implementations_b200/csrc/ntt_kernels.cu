@@ -466,6 +466,13 @@ extern "C" int ntt_cuda_d2h(int device, void *h_dst, const void *d_src, size_t b
   CU(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   return 0;
 }
+extern "C" int ntt_cuda_d2d(int device, void *d_dst, const void *d_src, size_t bytes, void *stream)
+{
+  DevGuard g(device);
+  if(!g.ok) return fail_msg("cudaSetDevice failed");
+  CU(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
 extern "C" int ntt_cuda_sync(int device, void *stream)
 {
   DevGuard g(device);
@@ -657,27 +664,37 @@ static bool use_fp64(const ntt_cuda_params_t &p, bool fwd)
 }
 
 template <int L, bool FWD, bool FP>
-static int launch_ring(int device, const ntt_cuda_params_t &p, uint64_t *d_a, size_t n_chunks, cudaStream_t st)
+static int launch_ring(int device, const ntt_cuda_params_t &p, uint64_t *d_a, size_t n_chunks, cudaStream_t st,
+                       const uint64_t *d_other = nullptr)
 {
   using C = RingCfg<L>;
-  auto        kern = k_ring<L, FWD>;
-  auto        kern_fp = k_ring_fp<L, FWD>;
-  static bool ready[64] = {false};
-  if(!ready[device & 63]) {
-    if(FP) {
-      CU(cudaFuncSetAttribute(kern_fp, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-    } else {
-      CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-    }
-    ready[device & 63] = true;
-  }
   CUtensorMap tm;
   if(make_block_tmap(&tm, d_a, n_chunks << L)) return -1;
   size_t grid = (size_t)sm_count(device) * C::CTAS;
   if(grid > n_chunks) grid = n_chunks;
-  if(FP) {
-    kern_fp<<<(unsigned)grid, C::THREADS, C::SMEM, st>>>(p, tm, n_chunks, d_a);
+  if(FP && FWD && d_other) {
+    auto        kern = k_ring_fp<L, true, true>;
+    static bool ready[64] = {false};
+    if(!ready[device & 63]) {
+      CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+      ready[device & 63] = true;
+    }
+    kern<<<(unsigned)grid, C::THREADS, C::SMEM, st>>>(p, tm, n_chunks, d_a, d_other);
+  } else if(FP) {
+    auto        kern = k_ring_fp<L, FWD, false>;
+    static bool ready[64] = {false};
+    if(!ready[device & 63]) {
+      CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+      ready[device & 63] = true;
+    }
+    kern<<<(unsigned)grid, C::THREADS, C::SMEM, st>>>(p, tm, n_chunks, d_a, nullptr);
   } else {
+    auto        kern = k_ring<L, FWD>;
+    static bool ready[64] = {false};
+    if(!ready[device & 63]) {
+      CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+      ready[device & 63] = true;
+    }
     kern<<<(unsigned)grid, C::THREADS, C::SMEM, st>>>(p, tm, n_chunks);
   }
   CU(cudaGetLastError());
@@ -687,18 +704,19 @@ static int launch_ring(int device, const ntt_cuda_params_t &p, uint64_t *d_a, si
 /* true if the ring kernel handled the chunk stage (lazy path, chunk of 2^12..2^14, pass-C tables present) */
 template <bool FWD>
 static int try_ring(int device, int L, const ntt_cuda_params_t &p, uint64_t *d_a, size_t n_chunks, cudaStream_t st,
-                    bool *done)
+                    bool *done, const uint64_t *d_other = nullptr)
 {
   *done = false;
   if(!ring_enabled() || !p.lazy || L < 12 || L > 14) return 0;
   if(!(FWD ? p.fwd_ct_wu : p.inv_ct_wu)) return 0;
   if(((uintptr_t)d_a & 127) != 0) return 0; /* TMA wants 128-byte aligned rows (cudaMalloc gives 256) */
+  if(d_other && !use_fp64(p, FWD)) return 0; /* the fused product exists on the FP64 kernel only */
   *done = true;
   if(use_fp64(p, FWD)) {
     switch(L) {
-      case 12: return launch_ring<12, FWD, true>(device, p, d_a, n_chunks, st);
-      case 13: return launch_ring<13, FWD, true>(device, p, d_a, n_chunks, st);
-      default: return launch_ring<14, FWD, true>(device, p, d_a, n_chunks, st);
+      case 12: return launch_ring<12, FWD, true>(device, p, d_a, n_chunks, st, d_other);
+      case 13: return launch_ring<13, FWD, true>(device, p, d_a, n_chunks, st, d_other);
+      default: return launch_ring<14, FWD, true>(device, p, d_a, n_chunks, st, d_other);
     }
   }
   switch(L) {
@@ -849,9 +867,13 @@ extern "C" int ntt_cuda_plan_inverse_bounds(ntt_cuda_params_t *p)
   return 0;
 }
 
+/* d_other != nullptr: also multiply pointwise by d_other (fused into the chunk kernel); *fused tells the caller
+ * whether that happened (it does on the FP64 ring kernel), otherwise nothing was multiplied. */
 template <bool EXACT>
-static int forward_impl(int device, const ntt_cuda_params_t &p, uint64_t *d_a, size_t batch, cudaStream_t st)
+static int forward_impl(int device, const ntt_cuda_params_t &p, uint64_t *d_a, size_t batch, cudaStream_t st,
+                        const uint64_t *d_other = nullptr, bool *fused = nullptr)
 {
+  if(fused) *fused = false;
   const Split sp = make_split((int)p.logn);
   uint32_t    s0 = 0;
   /* the FP64 chunk kernel wants inputs below 2^52: the last strided pass then hands over values below 2q */
@@ -864,6 +886,13 @@ static int forward_impl(int device, const ntt_cuda_params_t &p, uint64_t *d_a, s
   }
   if(!EXACT) {
     bool done = false;
+    if(d_other) {
+      if(try_ring<true>(device, sp.L, p, d_a, batch << s0, st, &done, d_other)) return -1;
+      if(done) {
+        if(fused) *fused = true;
+        return 0;
+      }
+    }
     if(try_ring<true>(device, sp.L, p, d_a, batch << s0, st, &done)) return -1;
     if(done) return 0;
   }
@@ -897,6 +926,23 @@ extern "C" int ntt_cuda_forward(int device, const ntt_cuda_params_t *p, uint64_t
   if(p->logn < 1 || p->logn > NTT_MAX_STAGES) return fail_msg("logn out of range");
   return p->lazy ? forward_impl<false>(device, *p, d_a, batch, (cudaStream_t)stream)
                  : forward_impl<true>(device, *p, d_a, batch, (cudaStream_t)stream);
+}
+
+/* forward transform of d_a, then d_a[i] *= d_other[i] mod q; *fused_out = 1 if the product was done inside the
+ * transform kernel, 0 if the caller still has to multiply (ntt_cuda_pointwise) */
+extern "C" int ntt_cuda_forward_mul(int device, const ntt_cuda_params_t *p, uint64_t *d_a, const uint64_t *d_other,
+                                    size_t batch, void *stream, int *fused_out)
+{
+  *fused_out = 0;
+  if(batch == 0) return 0;
+  DevGuard g(device);
+  if(!g.ok) return fail_msg("cudaSetDevice failed");
+  if(p->logn < 1 || p->logn > NTT_MAX_STAGES) return fail_msg("logn out of range");
+  bool      fused = false;
+  const int rc    = p->lazy ? forward_impl<false>(device, *p, d_a, batch, (cudaStream_t)stream, d_other, &fused)
+                            : forward_impl<true>(device, *p, d_a, batch, (cudaStream_t)stream);
+  *fused_out      = fused ? 1 : 0;
+  return rc;
 }
 
 extern "C" int ntt_cuda_inverse(int device, const ntt_cuda_params_t *p, uint64_t *d_a, size_t batch, void *stream)

@@ -158,11 +158,15 @@ __device__ long long g_trace[16 * 64 * 8]; /* [warp][poly][event] for CTA 0 */
 #define TRACE(ev)
 #endif
 
-template <int L, bool FWD>
+/* MUL (forward only): multiply the transform pointwise by `p_other` (another transform of the same shape,
+ * canonical residues) before it is written -- the NTT-domain product of a negacyclic polynomial multiply, fused
+ * into the second forward transform.  p_out: the array itself (the inverse writes its results directly). */
+template <int L, bool FWD, bool MUL = false>
 __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
   k_ring_fp(const __grid_constant__ ntt_cuda_params_t p, const __grid_constant__ CUtensorMap tmap, size_t n_chunks,
-            uint64_t *__restrict__ p_out)
+            uint64_t *__restrict__ p_out, const uint64_t *__restrict__ p_other)
 {
+  static_assert(FWD || !MUL, "the fused product belongs to the forward kernel");
   using C = RingCfg<L>;
   constexpr int NB = C::NB, RA = C::RA, SLOTS = C::SLOTS, T = C::THREADS, HALF = NB / 2;
   extern __shared__ uint8_t smem_raw[];
@@ -333,7 +337,15 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
 #pragma unroll
       for(int cc = 0; cc < 8; cc++) {
         ulonglong2 v;
-        if(FWD) {
+        if(FWD && MUL) {
+          /* other operand: same position of the other transform; o/q is rounded on the fly (it only steers the
+           * quotient estimate).  The product of a folded value with a residue below q is below 0.51q. */
+          const ulonglong2 o = __ldg(reinterpret_cast<const ulonglong2 *>(
+            p_other + (chunk << L) + (size_t)blk * 512 + lane * 16 + 2 * cc));
+          const double o0 = fp_from_u64(o.x), o1 = fp_from_u64(o.y);
+          v.x = fp_to_u64(fp_mul(fp_fold(x[2 * cc], c), o0, __dmul_rn(o0, c.qinv), c), c, p.q);
+          v.y = fp_to_u64(fp_mul(fp_fold(x[2 * cc + 1], c), o1, __dmul_rn(o1, c.qinv), c), c, p.q);
+        } else if(FWD) {
           v.x = fp_to_u64(fp_fold(x[2 * cc], c), c, p.q);
           v.y = fp_to_u64(fp_fold(x[2 * cc + 1], c), c, p.q);
         } else {

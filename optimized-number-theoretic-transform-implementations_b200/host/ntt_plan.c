@@ -454,10 +454,21 @@ int ntt_b200_negacyclic_mul_batch(const ntt_b200_plan_t *plan, uint64_t *d_c, ui
                                   size_t batch, void *stream)
 {
   if(check_batch(plan, d_a, 1) || check_batch(plan, d_b, 0) || check_batch(plan, d_c, 0)) return NTT_B200_ERROR;
-  if(ntt_b200_fwd_batch(plan, d_a, batch, stream)) return NTT_B200_ERROR;
-  if(ntt_b200_fwd_batch(plan, d_b, batch, stream)) return NTT_B200_ERROR;
-  if(ntt_b200_pointwise_mul_batch(plan, d_c, d_a, d_b, batch, stream)) return NTT_B200_ERROR;
-  return ntt_b200_inv_batch(plan, d_c, batch, stream);
+  /* the product lands in `prod` (the operand transformed second): prefer the one that aliases d_c */
+  uint64_t *first = d_a, *prod = d_b;
+  if(d_c == d_a) {
+    first = d_b;
+    prod  = d_a;
+  }
+  if(ntt_b200_fwd_batch(plan, first, batch, stream)) return NTT_B200_ERROR;
+  int fused = 0;
+  if(ntt_cuda_forward_mul(plan->device, &plan->params, prod, first, batch, stream, &fused))
+    return cuda_error("forward NTT with fused product");
+  if(!fused && ntt_b200_pointwise_mul_batch(plan, prod, prod, first, batch, stream)) return NTT_B200_ERROR;
+  if(ntt_b200_inv_batch(plan, prod, batch, stream)) return NTT_B200_ERROR;
+  if(prod != d_c && ntt_cuda_d2d(plan->device, d_c, prod, batch * (size_t)plan->N * 8, stream))
+    return cuda_error("result copy");
+  return NTT_B200_SUCCESS;
 }
 
 /* ---- host-resident batches ------------------------------------------------------------------------- */

@@ -1,0 +1,75 @@
+#!/usr/bin/env python
+"""Timings of BASELINE configs 3 and 4 on one GPU (they are parity-test cases in tests/, this adds the numbers):
+  config 3  CKKS-style RNS batch: N = 2^16, 48 limbs (largest 49-bit primes = 1 mod 2^17), B polynomials per limb
+  config 4  negacyclic polynomial multiply: N = 2^13, batch 16384 (fwd x2, pointwise, inverse; product fused)
+Rows are spot-checked against the oracle.  python tools/bench_configs.py [rns|polymul]"""
+import importlib, json, os, sys
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+ntt = importlib.import_module("optimized-number-theoretic-transform-implementations_b200")
+from oracle.pyoracle import Oracle
+orc = Oracle()
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+
+def timed(fn, steps=10, warm=3):
+    for _ in range(warm): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+if which in ("rns", "all"):
+    m, limbs, per = 16, 48, 32
+    N = 1 << m
+    qs, q = [], (1 << 49) + 1
+    q -= (q - 1) % (2 * N)
+    while len(qs) < limbs:
+        q -= 2 * N
+        if ntt.is_prime(q) and q <= (1 << 49) - 1024: qs.append(q)
+    plans, psis = [], []
+    for q in qs:
+        x = 2
+        while True:
+            psi = ntt.pow_mod(x, (q - 1) // (2 * N), q)
+            if ntt.pow_mod(psi, N, q) == q - 1: break
+            x += 1
+        psis.append(psi); plans.append(ntt.Plan.from_psi(N, q, psi))
+    rng = np.random.default_rng(2)
+    a = np.stack([rng.integers(0, q, size=(per, N), dtype=np.uint64) for q in qs])
+    d = torch.from_numpy(a.view(np.int64)).cuda()
+    ntt.fwd_rns(plans, d, per); f = d.cpu().numpy().view(np.uint64)
+    for l in (0, 47):
+        w, wc = orc.tables(N, qs[l], psis[l])
+        assert np.array_equal(f[l, 3], orc.fwd(a[l, 3], qs[l], w, wc)), "RNS limb %d differs from oracle" % l
+    ntt.inv_rns(plans, d, per); assert np.array_equal(d.cpu().numpy().view(np.uint64), a)
+    ms_f = timed(lambda: ntt.fwd_rns(plans, d, per)); ms_i = timed(lambda: ntt.inv_rns(plans, d, per))
+    n = limbs * per
+    print(json.dumps({"config": "RNS N=2^16 x 48 limbs x %d polys (1.5 GiB), 49-bit primes" % per, "fwd_ms": ms_f, "inv_ms": ms_i,
+                      "fwd_ntt_per_s": n / ms_f * 1e3, "inv_ntt_per_s": n / ms_i * 1e3,
+                      "fwd_frac_hbm_single_pass": n * 2 * N * 8 / (ms_f * 1e-3) / 6537.3e9}))
+    for p in plans: p.close()
+    del d
+
+if which in ("polymul", "all"):
+    m, batch, q, psi = 13, 16384, 0x1FFFFFC800001, 94912374482
+    N = 1 << m
+    plan = ntt.Plan.from_psi(N, q, psi)
+    rng = np.random.default_rng(3)
+    a = rng.integers(0, q, size=(batch, N), dtype=np.uint64); b = rng.integers(0, q, size=(batch, N), dtype=np.uint64)
+    da, db = torch.from_numpy(a.view(np.int64)).cuda(), torch.from_numpy(b.view(np.int64)).cuda()
+    dc = torch.empty_like(da)
+    plan.negacyclic_mul(dc, da, db, batch); c = dc.cpu().numpy().view(np.uint64)
+    w, wc = orc.tables(N, q, psi); wi, wic = orc.tables(N, q, orc.invmod(psi, q))
+    for r in (0, 9999):
+        prod = orc.pointwise_mul(orc.fwd(a[r], q, w, wc), orc.fwd(b[r], q, w, wc), q)
+        assert np.array_equal(c[r], orc.inv(prod, q, orc.invmod(N, q), wi, wic)), "polymul row %d differs from oracle" % r
+    def step():
+        plan.negacyclic_mul(da, da, db, batch)   # in place: result in da, db is work space
+    ms = timed(step)
+    ntt.configure("fp64", 0); ms_int = timed(step); ntt.configure("fp64", 1)
+    print(json.dumps({"config": "negacyclic polymul N=2^13 batch %d" % batch, "ms": ms, "polymul_per_s": batch / ms * 1e3,
+                      "frac_hbm_3N8": batch * 3 * N * 8 / (ms * 1e-3) / 6537.3e9, "ms_integer_unfused": ms_int}))
+    plan.close()
