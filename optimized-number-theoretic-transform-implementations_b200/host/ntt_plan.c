@@ -19,8 +19,9 @@ typedef unsigned __int128 u128;
 
 #define LAZY_MAX_QBITS 56 /* lazy path needs (4 + 10*24) * q < 2^64 */
 #define FP64_MAX_QBITS 49 /* FP64 path: bounds of csrc/ntt_ring_fp.cuh hold for q <= 2^49 - 1024 */
-#define HOST_PIPE_DEPTH 3
-#define HOST_PIPE_BYTES ((size_t)32 << 20)
+#define HOST_PIPE_DEPTH_MAX 8
+static int    g_pipe_depth = 4;                  /* chunks in flight, each on its own stream */
+static size_t g_pipe_bytes = (size_t)32 << 20;   /* bytes per chunk */
 
 struct ntt_b200_plan {
   int      device;
@@ -37,9 +38,10 @@ struct ntt_b200_plan {
   uint64_t *d_w, *d_w_con, *d_w_inv, *d_w_inv_con;
   /* host-buffer pipeline (created on first use) */
   pthread_mutex_t pipe_lock;
-  void *          pipe_stream[HOST_PIPE_DEPTH];
-  uint64_t *      pipe_buf[HOST_PIPE_DEPTH];
+  void *          pipe_stream[HOST_PIPE_DEPTH_MAX];
+  uint64_t *      pipe_buf[HOST_PIPE_DEPTH_MAX];
   size_t          pipe_polys;
+  int             pipe_depth;
 };
 
 static __thread char g_error[512];
@@ -126,7 +128,7 @@ static void plan_free(ntt_b200_plan_t *pl)
   for(size_t i = 0; i < sizeof(dev_ptrs) / sizeof(dev_ptrs[0]); i++) {
     if(dev_ptrs[i]) ntt_cuda_free(pl->device, dev_ptrs[i]);
   }
-  for(int i = 0; i < HOST_PIPE_DEPTH; i++) {
+  for(int i = 0; i < HOST_PIPE_DEPTH_MAX; i++) {
     if(pl->pipe_buf[i]) ntt_cuda_free(pl->device, pl->pipe_buf[i]);
     if(pl->pipe_stream[i]) ntt_cuda_stream_destroy(pl->device, pl->pipe_stream[i]);
   }
@@ -477,9 +479,13 @@ static int pipe_prepare(ntt_b200_plan_t *pl)
 {
   if(pl->pipe_polys) return NTT_B200_SUCCESS;
   const size_t poly_bytes = (size_t)pl->N * 8;
-  size_t       polys      = HOST_PIPE_BYTES / poly_bytes;
+  const char *ed = getenv("NTT_B200_PIPE_DEPTH"), *eb = getenv("NTT_B200_PIPE_MIB");
+  if(ed && atoi(ed) >= 1 && atoi(ed) <= HOST_PIPE_DEPTH_MAX) g_pipe_depth = atoi(ed);
+  if(eb && atoi(eb) >= 1 && atoi(eb) <= 1024) g_pipe_bytes = (size_t)atoi(eb) << 20;
+  pl->pipe_depth     = g_pipe_depth;
+  size_t       polys = g_pipe_bytes / poly_bytes;
   if(polys < 1) polys = 1;
-  for(int i = 0; i < HOST_PIPE_DEPTH; i++) {
+  for(int i = 0; i < pl->pipe_depth; i++) {
     if(ntt_cuda_stream_create(pl->device, &pl->pipe_stream[i])) return cuda_error("stream create");
     if(ntt_cuda_malloc(pl->device, (void **)&pl->pipe_buf[i], polys * poly_bytes)) return cuda_error("staging alloc");
   }
@@ -487,7 +493,7 @@ static int pipe_prepare(ntt_b200_plan_t *pl)
   return NTT_B200_SUCCESS;
 }
 
-/* H2D -> transform -> D2H in chunks, HOST_PIPE_DEPTH chunks in flight on their own streams */
+/* H2D -> transform -> D2H in chunks, pipe_depth chunks in flight on their own streams */
 static int host_apply(const ntt_b200_plan_t *plan, uint64_t *h_a, size_t batch, int inverse)
 {
   if(!plan) return set_error("plan is NULL%s", NULL);
@@ -514,9 +520,9 @@ static int host_apply(const ntt_b200_plan_t *plan, uint64_t *h_a, size_t batch, 
       rc = cuda_error("transform");
     if(!rc && ntt_cuda_d2h(pl->device, h_a + done * poly_words, d, bytes, st)) rc = cuda_error("D2H copy");
     done += take;
-    slot = (slot + 1) % HOST_PIPE_DEPTH;
+    slot = (slot + 1) % pl->pipe_depth;
   }
-  for(int i = 0; i < HOST_PIPE_DEPTH; i++) {
+  for(int i = 0; i < pl->pipe_depth; i++) {
     if(pl->pipe_stream[i] && ntt_cuda_sync(pl->device, pl->pipe_stream[i]) && !rc) rc = cuda_error("pipeline sync");
   }
   pthread_mutex_unlock(&pl->pipe_lock);

@@ -173,6 +173,40 @@ def test_exact_path_large_modulus(ntt, oracle):
         plan.close()
 
 
+@pytest.mark.parametrize("bits,m", [(50, 14), (50, 13), (53, 14), (56, 14), (56, 16), (49, 12)])
+def test_integer_ring_kernel_wide_moduli(ntt, oracle, bits, m):
+    """2^49 <= q < 2^56 runs the integer lazy ring kernel (no FP64): bounds, renormalisation schedule and the
+    final reduction are exercised with the largest primes of each size and inputs at the top of the contracts."""
+    N = 1 << m
+    q = (1 << bits) - ((1 << bits) - 1) % (2 * N)
+    while not oracle.is_prime(q) or q >= (1 << bits):
+        q -= 2 * N
+    x = 2
+    while True:
+        psi = oracle.powmod(x, (q - 1) // (2 * N), q)
+        if oracle.powmod(psi, N, q) == q - 1:
+            break
+        x += 1
+    t = CaseTables(oracle, m, q, psi, oracle.invmod(psi, q), oracle.invmod(N, q))
+    plan = ntt.Plan.from_psi(N, q, psi)
+    assert plan.is_lazy
+    batch = 160 if m <= 14 else 6
+    a = oracle.uniform(batch * N, 4 * q, bits).reshape(batch, N)
+    a[1, :] = 4 * q - 1
+    b = oracle.uniform(batch * N, 2 * q, bits + 1).reshape(batch, N)
+    b[1, :] = 2 * q - 1
+    da, db = to_dev(a), to_dev(b)
+    plan.fwd(da, batch)
+    plan.inv(db, batch)
+    fa, ib = to_host(da), to_host(db)
+    for r in (0, 1, batch - 1):
+        assert np.array_equal(fa[r], oracle.fwd(a[r], q, t.w, t.w_con)), "forward row %d" % r
+        assert np.array_equal(ib[r], oracle.inv(b[r], q, t.n_inv, t.w_inv, t.w_inv_con)), "inverse row %d" % r
+    plan.inv(da, batch)
+    assert np.array_equal(to_host(da), a % np.uint64(q))
+    plan.close()
+
+
 def test_synthetic_configs_golden(ntt, oracle, golden_synth):
     """The throughput parameter sets (49-bit q; N = 2^13, 2^14, 2^16) against reference-generated hashes."""
     for s in golden_synth:

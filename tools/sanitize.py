@@ -1,0 +1,26 @@
+"""Small end-to-end run of every kernel path for compute-sanitizer (memcheck / synccheck / initcheck)."""
+import importlib, os, sys, numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ntt = importlib.import_module("optimized-number-theoretic-transform-implementations_b200")
+q = 0x1FFFFFC800001
+for m, batch in ((12, 9), (13, 5), (14, 3), (15, 2), (8, 3)):
+    N = 1 << m
+    psi = ntt.min_primitive_root(N, q) if m <= 8 else None
+    if psi is None:
+        x = 2
+        while True:
+            psi = ntt.pow_mod(x, (q - 1) // (2 * N), q)
+            if ntt.pow_mod(psi, N, q) == q - 1: break
+            x += 1
+    plan = ntt.Plan.from_psi(N, q, psi)
+    a = np.random.default_rng(m).integers(0, q, size=(batch, N), dtype=np.uint64)
+    for ring, fp in ((1, 1), (1, 0), (0, 0)):
+        ntt.configure("ring", ring); ntt.configure("fp64", fp)
+        d = torch.from_numpy(a.view(np.int64)).cuda()
+        plan.fwd(d, batch); plan.inv(d, batch); torch.cuda.synchronize()
+        assert np.array_equal(d.cpu().numpy().view(np.uint64), a), (m, ring, fp)
+    ntt.configure("ring", 1); ntt.configure("fp64", 1)
+    d2 = torch.from_numpy(a.view(np.int64)).cuda(); d3 = torch.from_numpy(a.view(np.int64)).cuda()
+    plan.negacyclic_mul(d2, d2, d3, batch); torch.cuda.synchronize()
+    plan.close()
+print("sanitize run ok")
