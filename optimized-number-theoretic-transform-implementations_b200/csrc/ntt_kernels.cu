@@ -695,7 +695,7 @@ static int launch_ring(int device, const ntt_cuda_params_t &p, uint64_t *d_a, si
       CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
       ready[device & 63] = true;
     }
-    kern<<<(unsigned)grid, C::THREADS, C::SMEM, st>>>(p, tm, n_chunks);
+    kern<<<(unsigned)grid, C::THREADS, C::SMEM, st>>>(p, tm, n_chunks, d_a);
   }
   CU(cudaGetLastError());
   return 0;

@@ -244,7 +244,8 @@ __device__ __forceinline__ void ring_network_c(uint64_t (&x)[16], const ntt_cuda
 
 template <int L, bool FWD>
 __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
-  k_ring(const __grid_constant__ ntt_cuda_params_t p, const __grid_constant__ CUtensorMap tmap, size_t n_chunks)
+  k_ring(const __grid_constant__ ntt_cuda_params_t p, const __grid_constant__ CUtensorMap tmap, size_t n_chunks,
+         uint64_t *__restrict__ p_out)
 {
   using C = RingCfg<L>;
   constexpr int NB = C::NB, RA = C::RA, SLOTS = C::SLOTS, T = C::THREADS, HALF = NB / 2;
@@ -338,6 +339,34 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
       }
     };
 
+    /* inverse pass A: columns into registers, one __syncthreads, slots re-armed at once, results written from
+     * registers to global memory (256 contiguous bytes per warp store) -- see ntt_ring_fp.cuh for the why */
+    auto pass_a_inv = [&]() {
+      constexpr int COLS = 512 / T;
+      uint64_t      x[COLS][NB];
+#pragma unroll
+      for(int cidx = 0; cidx < COLS; cidx++) {
+        const uint32_t off = slot_off(tid + cidx * T);
+#pragma unroll
+        for(int b = 0; b < NB; b++)
+          x[cidx][b] = *reinterpret_cast<const uint64_t *>(ring_ptr + blk_slot(b) * 4096u + off);
+      }
+      __syncthreads();
+      if(lane == 0) {
+        issue_load(g0 + warp + SLOTS);
+        issue_load(g0 + warp + HALF + SLOTS);
+      }
+      uint64_t *gout = p_out + (chunk << L);
+#pragma unroll
+      for(int cidx = 0; cidx < COLS; cidx++) {
+        ring_network<RA, false>(x[cidx], p, s1, tw_wu, tw_qq);
+        const uint32_t j = tid + cidx * T;
+        const Red      rc{p.q, p.negq, p.red_shift, p.red_mu};
+#pragma unroll
+        for(int b = 0; b < NB; b++) gout[(size_t)b * 512 + j] = (s1 == 0) ? reduce_full(x[cidx][b], rc) : x[cidx][b];
+      }
+    };
+
     /* ---------- pass B: inside a block, 32 coefficients at stride 16; half-warp h owns block warp + h*HALF ---- */
     const uint32_t hb   = lane >> 4, jb = lane & 15u;
     const uint32_t blkB = warp + hb * HALF;
@@ -411,17 +440,7 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
       __syncwarp();
       pass_b();
       __syncthreads();
-      pass_a();
-      fence_proxy_async();
-      __syncthreads();
-      /* every warp drains and re-arms its own two blocks (one warp doing all NB stores serialises ~4 us) */
-      if(lane == 0) {
-        store_block(warp);
-        store_block(warp + HALF);
-        tma_wait_read_all();
-        issue_load(g0 + warp + SLOTS);
-        issue_load(g0 + warp + HALF + SLOTS);
-      }
+      pass_a_inv();
     }
   }
   /* the kernel may not exit while its bulk stores are still in flight */
