@@ -663,6 +663,10 @@ static bool use_fp64(const ntt_cuda_params_t &p, bool fwd)
   return fp64_enabled() && p.fp64 && (fwd ? p.fwd_ct_fd : p.inv_ct_fd) != nullptr;
 }
 
+/* Several small launches run side by side (RNS limbs on their own streams): each then takes only as many CTAs
+ * as gives every CTA a few chunks to pipeline, and leaves the other SMs to its neighbours.  0 = whole GPU. */
+static thread_local size_t g_min_chunks_per_cta = 0;
+
 template <int L, bool FWD, bool FP>
 static int launch_ring(int device, const ntt_cuda_params_t &p, uint64_t *d_a, size_t n_chunks, cudaStream_t st,
                        const uint64_t *d_other = nullptr)
@@ -672,6 +676,9 @@ static int launch_ring(int device, const ntt_cuda_params_t &p, uint64_t *d_a, si
   if(make_block_tmap(&tm, d_a, n_chunks << L)) return -1;
   size_t grid = (size_t)sm_count(device) * C::CTAS;
   if(grid > n_chunks) grid = n_chunks;
+  if(g_min_chunks_per_cta && grid * g_min_chunks_per_cta > n_chunks) {
+    grid = (n_chunks + g_min_chunks_per_cta - 1) / g_min_chunks_per_cta;
+  }
   if(FP && FWD && d_other) {
     auto        kern = k_ring_fp<L, true, true>;
     static bool ready[64] = {false};
@@ -978,6 +985,56 @@ extern "C" int ntt_cuda_tail(int device, const ntt_cuda_params_t *p, uint64_t *d
   }
   return inverse ? dispatch_strided_groups<false, true, 0>(device, (int)glog, *p, vbase, s0, first, n_groups, st)
                  : dispatch_strided_groups<true, true, 1>(device, (int)glog, *p, vbase, s0, first, n_groups, st);
+}
+
+/*
+ * RNS batch: limb l (its own modulus and tables, plist[l]) transforms `batch_per_limb` polynomials at
+ * d_a + l * batch_per_limb * N.  One launch per limb would leave each CTA one or two chunks, nothing to pipeline
+ * and a ragged tail, so the limbs are issued round-robin on a few internal streams, each launch sized to a
+ * fraction of the GPU (see g_min_chunks_per_cta); `stream` forks into them and joins again.
+ */
+extern "C" int ntt_cuda_rns(int device, const ntt_cuda_params_t *const *plist, size_t limbs, uint64_t *d_a,
+                            size_t batch_per_limb, int inverse, void *stream)
+{
+  if(limbs == 0 || batch_per_limb == 0) return 0;
+  DevGuard g(device);
+  if(!g.ok) return fail_msg("cudaSetDevice failed");
+  constexpr int       NS = 4;
+  static cudaStream_t side[64][NS];
+  static cudaEvent_t  fork_ev[64], join_ev[64][NS];
+  static bool         made[64] = {false};
+  const int           dv = device & 63;
+  if(!made[dv]) {
+    for(int i = 0; i < NS; i++) {
+      CU(cudaStreamCreateWithFlags(&side[dv][i], cudaStreamNonBlocking));
+      CU(cudaEventCreateWithFlags(&join_ev[dv][i], cudaEventDisableTiming));
+    }
+    CU(cudaEventCreateWithFlags(&fork_ev[dv], cudaEventDisableTiming));
+    made[dv] = true;
+  }
+  cudaStream_t user = (cudaStream_t)stream;
+  const size_t limb_words = batch_per_limb << plist[0]->logn;
+  const int    lanes = limbs < (size_t)NS ? (int)limbs : NS;
+  CU(cudaEventRecord(fork_ev[dv], user));
+  for(int i = 0; i < lanes; i++) CU(cudaStreamWaitEvent(side[dv][i], fork_ev[dv], 0));
+  int rc = 0;
+  g_min_chunks_per_cta = 4;
+  for(size_t l = 0; l < limbs && !rc; l++) {
+    const ntt_cuda_params_t &p  = *plist[l];
+    cudaStream_t             st = side[dv][l % lanes];
+    uint64_t *               d  = d_a + l * limb_words;
+    if(inverse) {
+      rc = p.lazy ? inverse_impl<false>(device, p, d, batch_per_limb, st) : inverse_impl<true>(device, p, d, batch_per_limb, st);
+    } else {
+      rc = p.lazy ? forward_impl<false>(device, p, d, batch_per_limb, st) : forward_impl<true>(device, p, d, batch_per_limb, st);
+    }
+  }
+  g_min_chunks_per_cta = 0;
+  for(int i = 0; i < lanes; i++) {
+    CU(cudaEventRecord(join_ev[dv][i], side[dv][i]));
+    CU(cudaStreamWaitEvent(user, join_ev[dv][i], 0));
+  }
+  return rc;
 }
 
 extern "C" int ntt_cuda_pointwise(int device, const ntt_cuda_params_t *p, uint64_t *d_c, const uint64_t *d_a,

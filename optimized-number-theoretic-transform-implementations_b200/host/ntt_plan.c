@@ -423,13 +423,19 @@ static int rns_apply(ntt_b200_plan_t *const *plans, size_t limbs, uint64_t *d_a,
     if(!plans[l] || plans[l]->N != plans[0]->N || plans[l]->device != plans[0]->device)
       return set_error("RNS plans must share N and device%s", NULL);
   }
-  const size_t limb_words = batch_per_limb * (size_t)plans[0]->N;
-  for(size_t l = 0; l < limbs; l++) {
-    const int rc = inverse ? ntt_b200_inv_batch(plans[l], d_a + l * limb_words, batch_per_limb, stream)
-                           : ntt_b200_fwd_batch(plans[l], d_a + l * limb_words, batch_per_limb, stream);
-    if(rc) return rc;
+  const ntt_cuda_params_t **plist = malloc(limbs * sizeof(*plist));
+  if(!plist) return set_error("out of host memory%s", NULL);
+  int rc = NTT_B200_SUCCESS;
+  for(size_t l = 0; l < limbs && !rc; l++) {
+    if(inverse ? !plans[l]->has_inv : !plans[l]->has_fwd)
+      rc = set_error("an RNS plan was created without the %s tables", inverse ? "inverse" : "forward");
+    plist[l] = &plans[l]->params;
   }
-  return NTT_B200_SUCCESS;
+  if(!rc && (((uintptr_t)d_a & 15) != 0)) rc = set_error("device data must be 16-byte aligned%s", NULL);
+  if(!rc && ntt_cuda_rns(plans[0]->device, plist, limbs, d_a, batch_per_limb, inverse, stream))
+    rc = cuda_error("RNS transform");
+  free(plist);
+  return rc;
 }
 
 int ntt_b200_fwd_rns(ntt_b200_plan_t *const *plans, size_t limbs, uint64_t *d_a, size_t batch_per_limb,
