@@ -46,7 +46,7 @@ const char *ntt_b200_version(void);
 /*
  * Kernel selection, for benchmarks and A/B parity tests only (every choice is a CUDA path):
  *   "ring" 0/1  persistent TMA ring kernel for chunks of 2^12..2^14 (default 1; 0 = generic smem kernel)
- *   "fp64" 0/1  run the ring kernel's butterflies on the FP64 pipe when q <= 2^49-1024 (default 1)
+ *   "fp64" 0/1  run the ring kernel's butterflies on the FP64 pipe when q <= 2^50-2048 (default 1)
  * The same switches are read from NTT_B200_NO_RING=1 / NTT_B200_NO_FP64=1 at first use.
  */
 int ntt_b200_configure(const char *key, int value);
@@ -111,7 +111,8 @@ int ntt_b200_inv_batch(const ntt_b200_plan_t *plan, uint64_t *d_a, size_t batch,
 
 /*
  * RNS form: limb l of every polynomial uses plans[l] (its own q).  d_a holds `limbs` consecutive
- * blocks of `batch_per_limb` polynomials.  All plans must share N and device.
+ * blocks of `batch_per_limb` polynomials.  All plans must share N and device.  The limbs run concurrently on
+ * internal streams that fork from and join back into `stream`.
  */
 int ntt_b200_fwd_rns(ntt_b200_plan_t *const *plans, size_t limbs, uint64_t *d_a, size_t batch_per_limb,
                      void *stream);

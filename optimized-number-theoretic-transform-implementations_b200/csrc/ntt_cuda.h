@@ -48,7 +48,7 @@ typedef struct ntt_cuda_params {
   const void *inv_ct_qq;
   /* FP64 path (q < 2^49, ntt_ring_fp.cuh): twiddles as (w, RN(w/q)) pairs of doubles, same index order as
    * wu/qq, plus their pass-C re-layout; q and RN(1/q); N^-1 and N^-1*w_inv[1] in the same form */
-  uint32_t    fp64;
+  uint32_t    fp64; /* 0: not eligible, 1: q <= 2^49-1024, 2: q <= 2^50-2048 (one more fold per pass) */
   uint32_t    pad0;
   double      q_fd, qinv_fd;
   double      ninv_fd[2], ninv_w1_fd[2];

@@ -679,22 +679,24 @@ static int launch_ring(int device, const ntt_cuda_params_t &p, uint64_t *d_a, si
   if(g_min_chunks_per_cta && grid * g_min_chunks_per_cta > n_chunks) {
     grid = (n_chunks + g_min_chunks_per_cta - 1) / g_min_chunks_per_cta;
   }
+  const bool q50 = p.fp64 == 2; /* 50-bit range schedule */
+#define NTT_LAUNCH_FP(MULV, Q50V)                                                                    \
+  do {                                                                                               \
+    auto        kern = k_ring_fp<L, FWD, MULV, Q50V>;                                                \
+    static bool ready[64] = {false};                                                                 \
+    if(!ready[device & 63]) {                                                                        \
+      CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));          \
+      ready[device & 63] = true;                                                                     \
+    }                                                                                                \
+    kern<<<(unsigned)grid, C::THREADS, C::SMEM, st>>>(p, tm, n_chunks, d_a, MULV ? d_other : nullptr); \
+  } while(0)
   if(FP && FWD && d_other) {
-    auto        kern = k_ring_fp<L, true, true>;
-    static bool ready[64] = {false};
-    if(!ready[device & 63]) {
-      CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-      ready[device & 63] = true;
-    }
-    kern<<<(unsigned)grid, C::THREADS, C::SMEM, st>>>(p, tm, n_chunks, d_a, d_other);
+    if(q50) NTT_LAUNCH_FP((FWD), true);
+    else NTT_LAUNCH_FP((FWD), false);
   } else if(FP) {
-    auto        kern = k_ring_fp<L, FWD, false>;
-    static bool ready[64] = {false};
-    if(!ready[device & 63]) {
-      CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-      ready[device & 63] = true;
-    }
-    kern<<<(unsigned)grid, C::THREADS, C::SMEM, st>>>(p, tm, n_chunks, d_a, nullptr);
+    if(q50) NTT_LAUNCH_FP(false, true);
+    else NTT_LAUNCH_FP(false, false);
+#undef NTT_LAUNCH_FP
   } else {
     auto        kern = k_ring<L, FWD>;
     static bool ready[64] = {false};

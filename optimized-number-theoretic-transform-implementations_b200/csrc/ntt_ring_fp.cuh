@@ -1,5 +1,5 @@
 /*
- * csrc/ntt_ring_fp.cuh -- the ring kernel with the butterflies on the FP64 pipe (q < 2^49).
+ * csrc/ntt_ring_fp.cuh -- the ring kernel with the butterflies on the FP64 pipe (q <= 2^50 - 2048).
  *
  * Why: on B200 the integer butterfly of ntt_device.cuh costs about 32 SM-cycles per warp (five 32x32->64
  * products dominate), while DFMA/DADD/DMUL issue at 61 lanes/clk/SM.  An exact FP64 formulation needs 8
@@ -16,10 +16,11 @@
  * so the residue is exact whatever c is; rounding only decides how large |t| gets:
  * |t| <= q*(0.5 + 1.01*|y|/2^52) as long as c really is rint(y*winv).  Butterflies are X' = X + t, Y' = X - t
  * (forward) and X' = X + Y, Y' = t(X - Y) (inverse) with no range correction; every pass first folds its
- * inputs to |v| <= q/2 + 6 (v - rint(v/q)*q, 3 instructions).  Forward, 5 stages from a fold: multiplied
- * operands stay below 3.3q < 2^51 (fp_mul's rounding trick is exact there), values below 4.2q.  Inverse, 4
- * stages from a fold: sums double to 8q + 96 < 2^52 (q <= 2^49 - 1024), which fp_mul_wide still rounds
- * exactly; 5-stage inverse passes fold once more after their first three stages.
+ * inputs to |v| <= q/2 + 6 (v - rint(v/q)*q, 3 instructions).  For q <= 2^49 - 1024: forward, 5 stages from a
+ * fold: multiplied operands stay below 3.3q < 2^51 (fp_mul's rounding trick is exact there), values below
+ * 4.2q; inverse, 4 stages from a fold: sums double to 8q + 96 < 2^52, which fp_mul_wide still rounds exactly;
+ * 5-stage inverse passes fold once more after their first three stages.  2^49 - 1024 < q <= 2^50 - 2048 runs a
+ * second schedule with one more fold per pass (see fp_network).
  * The last pass folds, adds q to negatives and converts back to u64: the output is the canonical residue in
  * [0,q), bit-identical to fwd_ntt_ref_harvey / inv_ntt_ref_harvey (include/ntt_reference.h:19-31,
  * src/ntt_reference.c:33-66).
@@ -97,10 +98,31 @@ __device__ __forceinline__ void fp_bfly_inv(double &x, double &y, double2 tw, co
   y              = WIDE ? fp_mul_wide(d, tw.x, tw.y, c) : fp_mul(d, tw.x, tw.y, c);
 }
 
-/* R-stage network; TWF(t) returns twiddle entry t = 2^u-1+sub of this group.  Inputs are folded first; a
- * 5-stage inverse network folds again after its first three stages.  FINAL: the inverse network ends with
- * global stage 0, whose two products carry N^-1 (harvey_bkw_butterfly_final, fast_mul_operators.h:94-106). */
-template <int R, bool FWD, bool FINAL, typename TWF>
+/* forward butterfly whose multiplied operand may reach 4q (50-bit schedule, fourth stage of pass C) */
+__device__ __forceinline__ void fp_bfly_fwd_wide(double &x, double &y, double2 tw, const FpC &c)
+{
+  const double t = fp_mul_wide(y, tw.x, tw.y, c);
+  y              = __dadd_rn(x, -t);
+  x              = __dadd_rn(x, t);
+}
+
+/*
+ * R-stage network; TWF(t) returns twiddle entry t = 2^u-1+sub of this group.  Inputs are folded first.
+ * FINAL: the inverse network ends with global stage 0, whose two products carry N^-1
+ * (harvey_bkw_butterfly_final, fast_mul_operators.h:94-106).
+ *
+ * Range schedules (n = stages since the last fold, values in units of q):
+ *   Q50 = false, q <= 2^49 - 1024 (q/2^52 < 1/8):
+ *     forward  bounds 0.5 -> 1.06 -> 1.70 -> 2.41 -> 3.21 -> 4.11: no second fold, operands < 3.3q < 2^51;
+ *     inverse  sums 0.5 -> 1 -> 2 -> 4 -> 8: differences reach 8q < 2^52 at n = 4 (wide rounding), a 5-stage
+ *              pass folds again after three stages.
+ *   Q50 = true, q <= 2^50 - 2048 (q/2^52 < 1/4):
+ *     forward  0.5 -> 1.13 -> 1.91 -> 2.88 -> 4.10: the operand is below 2q < 2^51 for n <= 3, below 4q < 2^52
+ *              at n = 4 (wide rounding), so a 5-stage pass folds again after three stages;
+ *     inverse  differences are 1, 2, 4 q at n = 1, 2, 3 (wide rounding from n = 2) and every pass folds
+ *              again after three stages.
+ */
+template <int R, bool FWD, bool FINAL, bool Q50, typename TWF>
 __device__ __forceinline__ void fp_network(double (&x)[1 << R], const FpC &c, const ntt_cuda_params_t &p, TWF twf)
 {
   constexpr int n = 1 << R;
@@ -110,21 +132,33 @@ __device__ __forceinline__ void fp_network(double (&x)[1 << R], const FpC &c, co
 #pragma unroll
     for(int u = 0; u < R; u++) {
       const int d = n >> (u + 1);
+      if(Q50 && R == 5 && u == 3) {
+#pragma unroll
+        for(int k = 0; k < n; k++) x[k] = fp_fold(x[k], c);
+      }
 #pragma unroll
       for(int sub = 0; sub < (1 << u); sub++) {
         const double2 tw = twf((1 << u) - 1 + sub);
 #pragma unroll
-        for(int k = 0; k < d; k++) fp_bfly_fwd(x[sub * 2 * d + k], x[sub * 2 * d + k + d], tw, c);
+        for(int k = 0; k < d; k++) {
+          if(Q50 && R == 4 && u == 3) fp_bfly_fwd_wide(x[sub * 2 * d + k], x[sub * 2 * d + k + d], tw, c);
+          else fp_bfly_fwd(x[sub * 2 * d + k], x[sub * 2 * d + k + d], tw, c);
+        }
       }
     }
   } else {
 #pragma unroll
     for(int u = R - 1; u >= 0; u--) {
       const int d = n >> (u + 1);
-      if(R == 5 && u == 1) {
+      /* second fold after three stages: every 5-stage pass, and 4-stage passes on the 50-bit schedule */
+      const bool refold = (R == 5 && u == 1) || (Q50 && R == 4 && u == 0);
+      if(refold) {
 #pragma unroll
         for(int k = 0; k < n; k++) x[k] = fp_fold(x[k], c);
       }
+      /* stages since the last fold, counting this one */
+      const int since = (R == 5) ? (u >= 2 ? 5 - u : 2 - u) : ((Q50 && R == 4 && u == 0) ? 1 : R - u);
+      const bool wide = Q50 ? since >= 2 : since >= 4;
       if(FINAL && u == 0) {
         const double2 a = make_double2(p.ninv_fd[0], p.ninv_fd[1]), b = make_double2(p.ninv_w1_fd[0], p.ninv_w1_fd[1]);
 #pragma unroll
@@ -139,8 +173,7 @@ __device__ __forceinline__ void fp_network(double (&x)[1 << R], const FpC &c, co
           const double2 tw = twf((1 << u) - 1 + sub);
 #pragma unroll
           for(int k = 0; k < d; k++) {
-            /* stages since the last fold: R = 4 reaches its fourth at u == 0 (|X - Y| up to 8q) */
-            if(R == 4 && u == 0) fp_bfly_inv<true>(x[sub * 2 * d + k], x[sub * 2 * d + k + d], tw, c);
+            if(wide) fp_bfly_inv<true>(x[sub * 2 * d + k], x[sub * 2 * d + k + d], tw, c);
             else fp_bfly_inv<false>(x[sub * 2 * d + k], x[sub * 2 * d + k + d], tw, c);
           }
         }
@@ -161,7 +194,7 @@ __device__ long long g_trace[16 * 64 * 8]; /* [warp][poly][event] for CTA 0 */
 /* MUL (forward only): multiply the transform pointwise by `p_other` (another transform of the same shape,
  * canonical residues) before it is written -- the NTT-domain product of a negacyclic polynomial multiply, fused
  * into the second forward transform.  p_out: the array itself (the inverse writes its results directly). */
-template <int L, bool FWD, bool MUL = false>
+template <int L, bool FWD, bool MUL = false, bool Q50 = false>
 __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
   k_ring_fp(const __grid_constant__ ntt_cuda_params_t p, const __grid_constant__ CUtensorMap tmap, size_t n_chunks,
             uint64_t *__restrict__ p_out, const uint64_t *__restrict__ p_other)
@@ -256,7 +289,7 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
 #pragma unroll
         for(int b = 0; b < NB; b++)
           x[b] = fp_from_u64(*reinterpret_cast<const uint64_t *>(ring_ptr + blk_slot(b) * 4096u + off));
-        fp_network<RA, true, false>(x, c, p, [&](int t) { return tw_s[t]; });
+        fp_network<RA, true, false, Q50>(x, c, p, [&](int t) { return tw_s[t]; });
 #pragma unroll
         for(int b = 0; b < NB; b++)
           *reinterpret_cast<double *>(ring_ptr + blk_slot(b) * 4096u + off) = x[b];
@@ -285,9 +318,9 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
 #pragma unroll
       for(int cidx = 0; cidx < COLS; cidx++) {
         if(s1 == 0) {
-          fp_network<RA, false, true>(x[cidx], c, p, [&](int t) { return tw_s[t]; });
+          fp_network<RA, false, true, Q50>(x[cidx], c, p, [&](int t) { return tw_s[t]; });
         } else {
-          fp_network<RA, false, false>(x[cidx], c, p, [&](int t) { return tw_s[t]; });
+          fp_network<RA, false, false, Q50>(x[cidx], c, p, [&](int t) { return tw_s[t]; });
         }
         const uint32_t j = tid + cidx * T;
 #pragma unroll
@@ -310,7 +343,7 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
 #pragma unroll
       for(int kk = 0; kk < 32; kk++)
         x[kk] = *reinterpret_cast<const double *>(base + kk * 128 + ((jc ^ (uint32_t)(kk & 7)) << 4));
-      fp_network<5, FWD, false>(x, c, p, [&](int t) { return tw[t]; });
+      fp_network<5, FWD, false, Q50>(x, c, p, [&](int t) { return tw[t]; });
 #pragma unroll
       for(int kk = 0; kk < 32; kk++)
         *reinterpret_cast<double *>(base + kk * 128 + ((jc ^ (uint32_t)(kk & 7)) << 4)) = x[kk];
@@ -333,7 +366,7 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
         issue_load(g0 + warp + SLOTS);
       }
       const double2 *tw = g_ct + ((size_t)cp * NB + blk) * 32 + lane;
-      fp_network<4, FWD, false>(x, c, p, [&](int t) { return __ldg(tw + (size_t)t * groups); });
+      fp_network<4, FWD, false, Q50>(x, c, p, [&](int t) { return __ldg(tw + (size_t)t * groups); });
 #pragma unroll
       for(int cc = 0; cc < 8; cc++) {
         ulonglong2 v;

@@ -18,7 +18,6 @@
 typedef unsigned __int128 u128;
 
 #define LAZY_MAX_QBITS 56 /* lazy path needs (4 + 10*24) * q < 2^64 */
-#define FP64_MAX_QBITS 49 /* FP64 path: bounds of csrc/ntt_ring_fp.cuh hold for q <= 2^49 - 1024 */
 #define HOST_PIPE_DEPTH_MAX 8
 static int    g_pipe_depth = 4;                  /* chunks in flight, each on its own stream */
 static size_t g_pipe_bytes = (size_t)32 << 20;   /* bytes per chunk */
@@ -114,7 +113,11 @@ static void fill_params(ntt_b200_plan_t *pl)
   p->red_shift = nttm_bitlen(pl->q) > 9 ? nttm_bitlen(pl->q) - 9 : 0;
   p->red_mu    = (uint32_t)((((u128)1) << (32 + p->red_shift)) / pl->q);
   /* FP64 ring kernel: q < 2^49 and a chunk size the ring kernel serves */
-  p->fp64    = (pl->q <= ((uint64_t)1 << FP64_MAX_QBITS) - 1024 && pl->logn >= 12) ? 1u : 0u;
+  p->fp64 = 0;
+  if(pl->logn >= 12) {
+    if(pl->q <= ((uint64_t)1 << 49) - 1024) p->fp64 = 1;
+    else if(pl->q <= ((uint64_t)1 << 50) - 2048) p->fp64 = 2;
+  }
   p->q_fd    = (double)pl->q;
   p->qinv_fd = 1.0 / (double)pl->q;
 }

@@ -254,15 +254,33 @@ def test_headline_config_roundtrip_and_linearity(ntt, oracle, golden_synth):
     plan.close()
 
 
-def test_kernel_paths_agree_on_full_batch(ntt, oracle, golden_synth):
+@pytest.mark.parametrize("bits", [49, 50])
+def test_kernel_paths_agree_on_full_batch(ntt, oracle, golden_synth, bits):
     """The three CUDA paths (FP64 ring, integer ring, generic smem kernel) must produce identical bytes on a
-    large batch, forward and inverse, on inputs at the edge of the contracts; rows are spot-checked vs the oracle."""
-    s = [x for x in golden_synth if x["m"] == 14][0]
-    N, q, batch = 1 << 14, s["q"], 2048
-    t = CaseTables(oracle, 14, q, s["psi"], s["psi_inv"], s["n_inv"])
-    plan = ntt.Plan.from_psi(N, q, s["psi"])
+    large batch, forward and inverse, on inputs at the edge of the contracts; rows are spot-checked vs the oracle.
+    bits = 49: the headline modulus (first FP64 range schedule); 50: the largest 50-bit prime (second schedule)."""
+    N, batch = 1 << 14, 2048
+    if bits == 49:
+        s = [x for x in golden_synth if x["m"] == 14][0]
+        q, psi = s["q"], s["psi"]
+    else:
+        q = (1 << 50) - ((1 << 50) - 1) % (2 * N)
+        while not oracle.is_prime(q) or q > (1 << 50) - 2048:
+            q -= 2 * N
+        x = 2
+        while True:
+            psi = oracle.powmod(x, (q - 1) // (2 * N), q)
+            if oracle.powmod(psi, N, q) == q - 1:
+                break
+            x += 1
+    t = CaseTables(oracle, 14, q, psi, oracle.invmod(psi, q), oracle.invmod(N, q))
+    plan = ntt.Plan.from_psi(N, q, psi)
     a4 = oracle.uniform(batch * N, 4 * q, 51).reshape(batch, N)   # forward contract [0,4q)
     a2 = oracle.uniform(batch * N, 2 * q, 52).reshape(batch, N)   # inverse contract [0,2q)
+    a4[7, :] = 4 * q - 1
+    a2[7, :] = 2 * q - 1
+    a4[8, ::2] = 0
+    a2[8, 1::2] = 0
     outs = {}
     try:
         for name, ring, fp in (("fp64", 1, 1), ("int", 1, 0), ("generic", 0, 0)):
@@ -278,7 +296,7 @@ def test_kernel_paths_agree_on_full_batch(ntt, oracle, golden_synth):
     for name in ("int", "generic"):
         assert np.array_equal(outs["fp64"][0], outs[name][0]), "forward: fp64 vs %s" % name
         assert np.array_equal(outs["fp64"][1], outs[name][1]), "inverse: fp64 vs %s" % name
-    for r in (0, 151, 206, 1023, 2047):
+    for r in (0, 7, 8, 151, 206, 1023, 2047):
         assert np.array_equal(outs["fp64"][0][r], oracle.fwd(a4[r], q, t.w, t.w_con))
         assert np.array_equal(outs["fp64"][1][r], oracle.inv(a2[r], q, t.n_inv, t.w_inv, t.w_inv_con))
     plan.close()
