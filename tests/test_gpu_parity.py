@@ -99,6 +99,22 @@ def test_fixture_case_edges_and_dbl(ntt, oracle, golden_cases, case_tables, idx)
     assert np.array_equal(a1, want) and np.array_equal(a2, want)
 
 
+def test_dropin_unaligned_host_pointers(ntt, oracle, case_tables):
+    """The reference's bench passes (64-byte aligned + 8) arrays (tests/test_cases.h:37-46, bench.c:160-186);
+    the reference-shaped entry points must take any 8-byte aligned host pointer."""
+    t = case_tables(9)
+    buf = np.zeros(t.N + 9, dtype=np.uint64)
+    off = ((8 - buf.ctypes.data % 64) % 64) // 8
+    a = buf[off:off + t.N]
+    assert a.ctypes.data % 64 == 8 and a.flags["C_CONTIGUOUS"]
+    src = oracle.uniform(t.N, t.q, 99)
+    a[:] = src
+    ntt.fwd_ntt_ref_harvey(a, t.N, t.q, t.w, t.w_con)
+    assert np.array_equal(a, oracle.fwd(src, t.q, t.w, t.w_con))
+    ntt.inv_ntt_ref_harvey(a, t.N, t.q, t.n_inv, t.n_inv_con, 64, t.w_inv, t.w_inv_con)
+    assert np.array_equal(a, src)
+
+
 def test_case0_full_vectors(ntt, golden_case0):
     g = golden_case0
     N, q = 1 << g["m"], g["q"]
