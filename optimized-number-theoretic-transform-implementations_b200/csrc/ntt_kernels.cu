@@ -614,13 +614,13 @@ static tmap_encode_fn tmap_encoder()
 
 /* The coefficient array seen as rows of 128 bytes (32 x u32); one TMA box = 32 rows = one 512-coefficient
  * block, written to shared memory with the 128-byte swizzle the passes are laid out for. */
-static int make_block_tmap(CUtensorMap *tm, uint64_t *d_a, size_t total_words)
+static int make_block_tmap(CUtensorMap *tm, uint64_t *d_a, size_t total_words, unsigned rows = 32)
 {
   tmap_encode_fn enc = tmap_encoder();
   if(!enc) return fail_msg("cuTensorMapEncodeTiled not available from the driver");
   const cuuint64_t dims[2]    = {32, (cuuint64_t)(total_words / 16)};
   const cuuint64_t strides[1] = {128};
-  const cuuint32_t box[2]     = {32, 32};
+  const cuuint32_t box[2]     = {32, rows};
   const cuuint32_t estr[2]    = {1, 1};
   const CUresult   r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, d_a, dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -672,8 +672,9 @@ static int launch_ring(int device, const ntt_cuda_params_t &p, uint64_t *d_a, si
                        const uint64_t *d_other = nullptr)
 {
   using C = RingCfg<L>;
-  CUtensorMap tm;
+  CUtensorMap tm, tm2;
   if(make_block_tmap(&tm, d_a, n_chunks << L)) return -1;
+  if(FP && make_block_tmap(&tm2, d_a, n_chunks << L, 32 * C::BOXB)) return -1; /* BOXB blocks per box */
   size_t grid = (size_t)sm_count(device) * C::CTAS;
   if(grid > n_chunks) grid = n_chunks;
   if(g_min_chunks_per_cta && grid * g_min_chunks_per_cta > n_chunks) {
@@ -688,7 +689,7 @@ static int launch_ring(int device, const ntt_cuda_params_t &p, uint64_t *d_a, si
       CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));          \
       ready[device & 63] = true;                                                                     \
     }                                                                                                \
-    kern<<<(unsigned)grid, C::THREADS, C::SMEM, st>>>(p, tm, n_chunks, d_a, MULV ? d_other : nullptr); \
+    kern<<<(unsigned)grid, C::THREADS, C::SMEM, st>>>(p, tm, tm2, n_chunks, d_a, MULV ? d_other : nullptr); \
   } while(0)
   if(FP && FWD && d_other) {
     if(q50) NTT_LAUNCH_FP((FWD), true);

@@ -63,6 +63,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
     "r"(parity)
     : "memory");
 }
+/* named barrier 1: arrive without waiting / wait for `count` threads (producer-consumer hand-off inside the CTA) */
+__device__ __forceinline__ void named_arrive(uint32_t count) { asm volatile("bar.arrive 1, %0;" ::"r"(count) : "memory"); }
+__device__ __forceinline__ void named_sync(uint32_t count) { asm volatile("bar.sync 1, %0;" ::"r"(count) : "memory"); }
 __device__ __forceinline__ void fence_barrier_init()
 {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -119,9 +122,12 @@ struct RingCfg {
   /* 228 KiB per SM, 1 KiB reserved per resident CTA, at most 227 KiB per CTA */
   static constexpr int PER_CTA  = 233472 / CTAS - 1024;
   static constexpr int BUDGET   = PER_CTA < 232448 ? PER_CTA : 232448;
-  static constexpr int SLOTS    = (BUDGET - TW_BYTES - 1024 - 64) / 4096;  /* 50 / 24 / 12 for L = 14 / 13 / 12 */
+  /* the inverse re-arms a dead polynomial with four big TMA boxes of BOXB = NB/4 adjacent blocks each
+   * (BOXB*32 rows <= 256): the ring depth is a multiple of BOXB so that a box never wraps */
+  static constexpr int BOXB     = NB / 4;
+  static constexpr int SLOTS    = ((BUDGET - TW_BYTES - 1024 - 64) / 4096) / BOXB * BOXB; /* 48 / 24 / 12 for L = 14 / 13 / 12 */
   static constexpr int SMEM     = SLOTS * 4096 + 1024 /* alignment slack */ + TW_BYTES + 64 /* 8 barriers */;
-  static_assert(SLOTS > NB && 4 * NB > SLOTS, "ring depth vs. mbarrier reuse distance");
+  static_assert(SLOTS > NB && 4 * NB > SLOTS && SLOTS % BOXB == 0, "ring depth vs. mbarrier reuse distance");
 };
 
 /* byte offset of coefficient o (0..511) inside a 4-KiB slot under TMA SWIZZLE_128B (rows of 128 bytes) */

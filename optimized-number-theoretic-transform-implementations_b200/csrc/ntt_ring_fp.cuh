@@ -196,8 +196,9 @@ __device__ long long g_trace[16 * 64 * 8]; /* [warp][poly][event] for CTA 0 */
  * into the second forward transform.  p_out: the array itself (the inverse writes its results directly). */
 template <int L, bool FWD, bool MUL = false, bool Q50 = false>
 __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
-  k_ring_fp(const __grid_constant__ ntt_cuda_params_t p, const __grid_constant__ CUtensorMap tmap, size_t n_chunks,
-            uint64_t *__restrict__ p_out, const uint64_t *__restrict__ p_other)
+  k_ring_fp(const __grid_constant__ ntt_cuda_params_t p, const __grid_constant__ CUtensorMap tmap,
+            const __grid_constant__ CUtensorMap tmap2, size_t n_chunks, uint64_t *__restrict__ p_out,
+            const uint64_t *__restrict__ p_other)
 {
   static_assert(FWD || !MUL, "the fused product belongs to the forward kernel");
   using C = RingCfg<L>;
@@ -231,13 +232,32 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
     tma_load_block(slot_addr(g), &tmap, (int)((chunk << (L - 4)) + b * 32u), bar);
   };
 
+  /* inverse: all slots of a polynomial die together, so they are re-armed with four boxes of BOXB adjacent
+   * blocks (tmap2: BOXB*32 rows, up to 32 KiB) -- four TMA instructions instead of NB on the critical path of
+   * pass A; measured, a TMA load costs its issuing thread about 130 cycles whatever the box size. */
+  auto issue_box = [&](size_t g) { /* g multiple of BOXB: blocks g .. g+BOXB-1, adjacent slots, one half-barrier */
+    if(g >= my_blocks) return;
+    const size_t   k     = g / NB;
+    const uint32_t b     = (uint32_t)(g % NB);
+    const size_t   chunk = blockIdx.x + k * gridDim.x;
+    const uint32_t bar = bars + 8u * (2u * (uint32_t)(k % C::NBAR) + (b >= (uint32_t)HALF ? 1u : 0u));
+    mbar_arrive_expect_tx(bar, 4096u * C::BOXB);
+    tma_load_block(slot_addr(g), &tmap2, (int)((chunk << (L - 4)) + b * 32u), bar);
+  };
+
   if(tid == 0) {
     tma_prefetch_desc(&tmap);
-    for(int i = 0; i < 2 * C::NBAR; i++) mbar_init(bars + 8u * i, HALF);
+    tma_prefetch_desc(&tmap2);
+    /* forward: one arrival per block; inverse: one per box, two boxes per half */
+    for(int i = 0; i < 2 * C::NBAR; i++) mbar_init(bars + 8u * i, FWD ? HALF : 2);
     fence_barrier_init();
   }
   __syncthreads();
-  for(uint32_t g = tid; g < (uint32_t)SLOTS; g += T) issue_load(g);
+  if(FWD) {
+    for(uint32_t g = tid; g < (uint32_t)SLOTS; g += T) issue_load(g);
+  } else {
+    for(uint32_t g = C::BOXB * tid; g < (uint32_t)SLOTS; g += C::BOXB * T) issue_box(g);
+  }
   uint32_t cached_cp = 0xffffffffu;
   for(size_t k = 0; k < my_polys; k++) {
     const size_t   chunk = blockIdx.x + k * gridDim.x;
@@ -295,8 +315,8 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
           *reinterpret_cast<double *>(ring_ptr + blk_slot(b) * 4096u + off) = x[b];
       }
     };
-    /* pass A, inverse: last pass.  Every thread first pulls its column(s) into registers; after one
-     * __syncthreads the polynomial's slots are dead and are re-armed at once (the next polynomials' blocks get
+    /* pass A, inverse: last pass.  Every thread first pulls its column(s) into registers; once all have, the
+     * polynomial's slots are dead and are re-armed at once (the next polynomials' blocks get
      * a whole pass of lead time), and the results go from registers straight to global memory: column j of
      * block b is word b*512+j, so a warp writes 256 contiguous bytes per store instruction.  No TMA store,
      * no proxy fence, no drain wait on this side. */
@@ -309,26 +329,35 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
 #pragma unroll
         for(int b = 0; b < NB; b++) x[cidx][b] = *reinterpret_cast<const double *>(ring_ptr + blk_slot(b) * 4096u + off);
       }
-      __syncthreads();
-      if(lane == 0) {
-        issue_load(g0 + warp + SLOTS);
-        issue_load(g0 + warp + HALF + SLOTS);
+      /* the slots may be overwritten once EVERY warp has pulled its columns: warp 0 waits for that (named
+       * barrier, the other warps only arrive and go straight on to their butterflies) and re-arms the ring */
+      if(warp == 0) {
+        named_sync(T);
+        if(lane < 4) issue_box(g0 + C::BOXB * lane + SLOTS);
+        __syncwarp();
+      } else {
+        named_arrive(T);
       }
+      TRACE(6);
       uint64_t *gout = p_out + (chunk << L);
+      if(s1 == 0) {
+        /* the chunk is the whole polynomial: global stage 0 with N^-1 is part of this pass and its products
+         * (|v| < q) are final */
 #pragma unroll
-      for(int cidx = 0; cidx < COLS; cidx++) {
-        if(s1 == 0) {
+        for(int cidx = 0; cidx < COLS; cidx++) {
           fp_network<RA, false, true, Q50>(x[cidx], c, p, [&](int t) { return tw_s[t]; });
-        } else {
-          fp_network<RA, false, false, Q50>(x[cidx], c, p, [&](int t) { return tw_s[t]; });
-        }
-        const uint32_t j = tid + cidx * T;
+          const uint32_t j = tid + cidx * T;
 #pragma unroll
-        for(int b = 0; b < NB; b++) {
-          /* with s1 == 0 the values are final products (|v| < q); otherwise fold first.  Either way the
-           * canonical residue goes out (the strided inverse passes that follow accept [0,2q)). */
-          const double v = (s1 == 0) ? x[cidx][b] : fp_fold(x[cidx][b], c);
-          gout[(size_t)b * 512 + j] = fp_to_u64(v, c, p.q);
+          for(int b = 0; b < NB; b++) gout[(size_t)b * 512 + j] = fp_to_u64(x[cidx][b], c, p.q);
+        }
+      } else {
+        /* strided inverse passes follow (they accept [0,2q)): fold and hand over the canonical residue */
+#pragma unroll
+        for(int cidx = 0; cidx < COLS; cidx++) {
+          fp_network<RA, false, false, Q50>(x[cidx], c, p, [&](int t) { return tw_s[t]; });
+          const uint32_t j = tid + cidx * T;
+#pragma unroll
+          for(int b = 0; b < NB; b++) gout[(size_t)b * 512 + j] = fp_to_u64(fp_fold(x[cidx][b], c), c, p.q);
         }
       }
     };
@@ -430,7 +459,6 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
       __syncthreads();
       TRACE(5);
       pass_a_inv();
-      TRACE(6);
       TRACE(7);
     }
   }
