@@ -270,26 +270,27 @@ def test_headline_config_roundtrip_and_linearity(ntt, oracle, golden_synth):
     plan.close()
 
 
-@pytest.mark.parametrize("bits", [49, 50])
-def test_kernel_paths_agree_on_full_batch(ntt, oracle, golden_synth, bits):
+@pytest.mark.parametrize("m,bits", [(14, 49), (14, 50), (13, 49), (13, 50), (12, 49), (12, 50), (16, 49), (16, 50)])
+def test_kernel_paths_agree_on_full_batch(ntt, oracle, golden_synth, m, bits):
     """The three CUDA paths (FP64 ring, integer ring, generic smem kernel) must produce identical bytes on a
     large batch, forward and inverse, on inputs at the edge of the contracts; rows are spot-checked vs the oracle.
-    bits = 49: the headline modulus (first FP64 range schedule); 50: the largest 50-bit prime (second schedule)."""
-    N, batch = 1 << 14, 2048
+    bits = 49: the headline modulus (first FP64 range schedule); 50: the largest 50-bit prime (second schedule).
+    m = 12, 13, 14: the three ring-kernel geometries; 16: strided pass + 2^14 chunks."""
+    N = 1 << m
+    batch = (1 << 25) >> m  # 2^25 coefficients per direction: 2048 polynomials at N = 2^14
     if bits == 49:
-        s = [x for x in golden_synth if x["m"] == 14][0]
-        q, psi = s["q"], s["psi"]
+        q = 0x1FFFFFC800001
     else:
         q = (1 << 50) - ((1 << 50) - 1) % (2 * N)
         while not oracle.is_prime(q) or q > (1 << 50) - 2048:
             q -= 2 * N
-        x = 2
-        while True:
-            psi = oracle.powmod(x, (q - 1) // (2 * N), q)
-            if oracle.powmod(psi, N, q) == q - 1:
-                break
-            x += 1
-    t = CaseTables(oracle, 14, q, psi, oracle.invmod(psi, q), oracle.invmod(N, q))
+    x = 2
+    while True:
+        psi = oracle.powmod(x, (q - 1) // (2 * N), q)
+        if oracle.powmod(psi, N, q) == q - 1:
+            break
+        x += 1
+    t = CaseTables(oracle, m, q, psi, oracle.invmod(psi, q), oracle.invmod(N, q))
     plan = ntt.Plan.from_psi(N, q, psi)
     a4 = oracle.uniform(batch * N, 4 * q, 51).reshape(batch, N)   # forward contract [0,4q)
     a2 = oracle.uniform(batch * N, 2 * q, 52).reshape(batch, N)   # inverse contract [0,2q)
@@ -312,7 +313,7 @@ def test_kernel_paths_agree_on_full_batch(ntt, oracle, golden_synth, bits):
     for name in ("int", "generic"):
         assert np.array_equal(outs["fp64"][0], outs[name][0]), "forward: fp64 vs %s" % name
         assert np.array_equal(outs["fp64"][1], outs[name][1]), "inverse: fp64 vs %s" % name
-    for r in (0, 7, 8, 151, 206, 1023, 2047):
+    for r in (0, 7, 8, batch // 3, batch - 1):
         assert np.array_equal(outs["fp64"][0][r], oracle.fwd(a4[r], q, t.w, t.w_con))
         assert np.array_equal(outs["fp64"][1][r], oracle.inv(a2[r], q, t.n_inv, t.w_inv, t.w_inv_con))
     plan.close()
@@ -368,6 +369,20 @@ def test_negacyclic_polymul(ntt, oracle, golden_synth):
     prod = oracle.pointwise_mul(fa, fb, q).reshape(batch, N)
     want = oracle.inv(prod, q, t.n_inv, t.w_inv, t.w_inv_con)
     assert np.array_equal(to_host(dc), want)
+    # the fused product (FP64 kernel) against the unfused integer pipeline on a large batch, byte for byte
+    big = 2048
+    a = oracle.uniform(big * N, q, 33).reshape(big, N)
+    b = oracle.uniform(big * N, q, 34).reshape(big, N)
+    res = {}
+    try:
+        for name, fp in (("fused", 1), ("unfused", 0)):
+            ntt.configure("fp64", fp)
+            da, db = to_dev(a), to_dev(b)
+            plan.negacyclic_mul(da, da, db, big)
+            res[name] = to_host(da)
+    finally:
+        ntt.configure("fp64", 1)
+    assert np.array_equal(res["fused"], res["unfused"])
     plan.close()
 
 
