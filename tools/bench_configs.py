@@ -11,6 +11,13 @@ ntt = importlib.import_module("optimized-number-theoretic-transform-implementati
 from oracle.pyoracle import Oracle
 orc = Oracle()
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
+# under torchrun the RNS limbs are sharded contiguously across the ranks (no collective on the data path)
+rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local)
+if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+sharding = importlib.import_module("optimized-number-theoretic-transform-implementations_b200.sharding")
 
 def timed(fn, steps=10, warm=3):
     for _ in range(warm): fn()
@@ -29,6 +36,8 @@ if which in ("rns", "all"):
     while len(qs) < limbs:
         q -= 2 * N
         if ntt.is_prime(q) and q <= (1 << 49) - 1024: qs.append(q)
+    lb, le = sharding.shard_range(limbs, rank, world)
+    all_limbs, qs, limbs = limbs, qs[lb:le], le - lb
     plans, psis = [], []
     for q in qs:
         x = 2
@@ -36,24 +45,28 @@ if which in ("rns", "all"):
             psi = ntt.pow_mod(x, (q - 1) // (2 * N), q)
             if ntt.pow_mod(psi, N, q) == q - 1: break
             x += 1
-        psis.append(psi); plans.append(ntt.Plan.from_psi(N, q, psi))
+        psis.append(psi); plans.append(ntt.Plan.from_psi(N, q, psi, device=local))
     rng = np.random.default_rng(2)
     a = np.stack([rng.integers(0, q, size=(per, N), dtype=np.uint64) for q in qs])
     d = torch.from_numpy(a.view(np.int64)).cuda()
     ntt.fwd_rns(plans, d, per); f = d.cpu().numpy().view(np.uint64)
-    for l in (0, 47):
+    for l in (0, limbs - 1):
         w, wc = orc.tables(N, qs[l], psis[l])
         assert np.array_equal(f[l, 3], orc.fwd(a[l, 3], qs[l], w, wc)), "RNS limb %d differs from oracle" % l
     ntt.inv_rns(plans, d, per); assert np.array_equal(d.cpu().numpy().view(np.uint64), a)
+    if world > 1: dist.barrier()
     ms_f = timed(lambda: ntt.fwd_rns(plans, d, per)); ms_i = timed(lambda: ntt.inv_rns(plans, d, per))
-    n = limbs * per
-    print(json.dumps({"config": "RNS N=2^16 x 48 limbs x %d polys (1.5 GiB), 49-bit primes" % per, "fwd_ms": ms_f, "inv_ms": ms_i,
-                      "fwd_ntt_per_s": n / ms_f * 1e3, "inv_ntt_per_s": n / ms_i * 1e3,
-                      "fwd_frac_hbm_single_pass": n * 2 * N * 8 / (ms_f * 1e-3) / 6537.3e9}))
+    if world > 1:
+        tt = torch.tensor([ms_f, ms_i], device="cuda"); dist.all_reduce(tt, op=dist.ReduceOp.MAX); ms_f, ms_i = tt.tolist()
+    n = all_limbs * per
+    if rank == 0:
+        print(json.dumps({"config": "RNS N=2^16 x %d limbs x %d polys, 49-bit primes, limbs sharded over %d GPU(s)" % (all_limbs, per, world),
+                          "fwd_ms": ms_f, "inv_ms": ms_i, "fwd_ntt_per_s": n / ms_f * 1e3, "inv_ntt_per_s": n / ms_i * 1e3,
+                          "fwd_frac_hbm_single_pass_per_gpu": n * 2 * N * 8 / (ms_f * 1e-3) / 6537.3e9 / world}))
     for p in plans: p.close()
     del d
 
-if which in ("polymul", "all"):
+if which in ("polymul", "all") and rank == 0:
     m, batch, q, psi = 13, 16384, 0x1FFFFFC800001, 94912374482
     N = 1 << m
     plan = ntt.Plan.from_psi(N, q, psi)
@@ -73,3 +86,6 @@ if which in ("polymul", "all"):
     print(json.dumps({"config": "negacyclic polymul N=2^13 batch %d" % batch, "ms": ms, "polymul_per_s": batch / ms * 1e3,
                       "frac_hbm_3N8": batch * 3 * N * 8 / (ms * 1e-3) / 6537.3e9, "ms_integer_unfused": ms_int}))
     plan.close()
+
+if world > 1:
+    dist.destroy_process_group()
