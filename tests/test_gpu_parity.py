@@ -319,6 +319,50 @@ def test_kernel_paths_agree_on_full_batch(ntt, oracle, golden_synth, m, bits):
     plan.close()
 
 
+@pytest.mark.parametrize("bits", [49, 50])
+def test_fp64_path_structured_inputs(ntt, oracle, bits):
+    """Structured vectors that push sums and differences to their extremes (constant, alternating, half-filled,
+    single spikes, top-of-range), through the FP64 ring kernel at N = 2^14, against the oracle."""
+    m, N = 14, 1 << 14
+    if bits == 49:
+        q = 0x1FFFFFC800001
+    else:
+        q = (1 << 50) - ((1 << 50) - 1) % (2 * N)
+        while not oracle.is_prime(q) or q > (1 << 50) - 2048:
+            q -= 2 * N
+    x = 2
+    while True:
+        psi = oracle.powmod(x, (q - 1) // (2 * N), q)
+        if oracle.powmod(psi, N, q) == q - 1:
+            break
+        x += 1
+    t = CaseTables(oracle, m, q, psi, oracle.invmod(psi, q), oracle.invmod(N, q))
+    plan = ntt.Plan.from_psi(N, q, psi)
+    idx = np.arange(N)
+    rows = []
+    for top in (q - 1, 4 * q - 1):
+        rows += [np.full(N, top), np.where(idx % 2 == 0, top, 0), np.where(idx < N // 2, top, 0),
+                 np.where(idx % 4 < 2, top, 1), np.where((idx >> 7) % 2 == 0, top, 0)]
+    for pos in (0, 1, N // 2, N - 1):
+        v = np.zeros(N); v[pos] = q - 1; rows.append(v)
+    rows.append(idx % q); rows.append((q - 1 - idx) % q)
+    a = np.stack(rows).astype(np.uint64)
+    batch = a.shape[0]
+    d = to_dev(a)
+    plan.fwd(d, batch)
+    f = to_host(d)
+    assert np.array_equal(f, oracle.fwd(a, q, t.w, t.w_con))
+    # the same vectors as NTT-domain input of the inverse (contract [0,2q)), and the inverse of their transforms
+    b = np.minimum(a, np.uint64(2 * q - 1))
+    d = to_dev(b)
+    plan.inv(d, batch)
+    assert np.array_equal(to_host(d), oracle.inv(b, q, t.n_inv, t.w_inv, t.w_inv_con))
+    d = to_dev(f)
+    plan.inv(d, batch)
+    assert np.array_equal(to_host(d), a % np.uint64(q))
+    plan.close()
+
+
 def test_rns_limbs(ntt, oracle):
     """BASELINE config 3 shape (scaled down): N=2^16, several ~50-bit limbs, each with its own q."""
     N, m, limbs, per = 1 << 16, 16, 3, 2
