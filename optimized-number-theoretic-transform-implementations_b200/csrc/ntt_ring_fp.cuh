@@ -13,8 +13,11 @@
  *     h = RN(w*y),  l = fma(w, y, -h)       (error-free product: w*y = h + l exactly)
  *     d = fma(-c, q, h)                     (exact: |h - c*q| < 2^53)
  *     t = d + l                             (exact)  =>  t = w*y - c*q == w*y (mod q), an integer
- * so the residue is exact whatever c is; rounding only decides how large |t| gets:
- * |t| <= q*(0.5 + 1.01*|y|/2^52) as long as c really is rint(y*winv).  Butterflies are X' = X + t, Y' = X - t
+ * so the residue is exact whatever c is; rounding only decides how large |t| gets.  winv is within 2^-54 of
+ * w/q, so |t| <= q*(1/2 + |y|*2^-54) for fp_mul (one fused rounding to an integer) and
+ * |t| <= q*(1/2 + min(|y|*2^-53, 1/4) + |y|*2^-54) < q for fp_mul_wide (|y| < 2^52) -- as long as c really is
+ * an integer (tests/test_fp64_arith_model.py replays both and the schedules below on the CPU).
+ * Butterflies are X' = X + t, Y' = X - t
  * (forward) and X' = X + Y, Y' = t(X - Y) (inverse) with no range correction; every pass first folds its
  * inputs to |v| <= q/2 + 6 (v - rint(v/q)*q, 3 instructions).  For q <= 2^49 - 1024: forward, 5 stages from a
  * fold: multiplied operands stay below 3.3q < 2^51 (fp_mul's rounding trick is exact there), values below
@@ -160,6 +163,8 @@ __device__ __forceinline__ void fp_network(double (&x)[1 << R], const FpC &c, co
       const int since = (R == 5) ? (u >= 2 ? 5 - u : 2 - u) : ((Q50 && R == 4 && u == 0) ? 1 : R - u);
       const bool wide = Q50 ? since >= 2 : since >= 4;
       if(FINAL && u == 0) {
+        /* sums reach 8q (49-bit, R = 4) or 4q (50-bit, R = 3): still below 2^52, so the products are below q in
+         * magnitude (bound in the header) and are converted without another fold */
         const double2 a = make_double2(p.ninv_fd[0], p.ninv_fd[1]), b = make_double2(p.ninv_w1_fd[0], p.ninv_w1_fd[1]);
 #pragma unroll
         for(int k = 0; k < d; k++) {
