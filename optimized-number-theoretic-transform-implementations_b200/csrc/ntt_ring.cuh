@@ -125,9 +125,10 @@ struct RingCfg {
   /* the inverse re-arms a dead polynomial with four big TMA boxes of BOXB = NB/4 adjacent blocks each
    * (BOXB*32 rows <= 256): the ring depth is a multiple of BOXB so that a box never wraps */
   static constexpr int BOXB     = NB / 4;
-  static constexpr int SLOTS    = ((BUDGET - TW_BYTES - 1024 - 64) / 4096) / BOXB * BOXB; /* 48 / 24 / 12 for L = 14 / 13 / 12 */
+  static constexpr int SLOTS    = ((BUDGET - TW_BYTES - 1024 - 64) / 4096) / (NB / 2) * (NB / 2); /* 48 / 24 / 12 for L = 14 / 13 / 12 */
   static constexpr int SMEM     = SLOTS * 4096 + 1024 /* alignment slack */ + TW_BYTES + 64 /* 8 barriers */;
   static_assert(SLOTS > NB && 4 * NB > SLOTS && SLOTS % BOXB == 0, "ring depth vs. mbarrier reuse distance");
+  static_assert(SLOTS % (NB / 2) == 0, "half a polynomial must not wrap around the ring (blk_slot)");
 };
 
 /* byte offset of coefficient o (0..511) inside a 4-KiB slot under TMA SWIZZLE_128B (rows of 128 bytes) */
@@ -291,6 +292,7 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
   for(uint32_t g = tid; g < (uint32_t)SLOTS; g += T) issue_load(g);
 
   uint32_t cached_cp = 0xffffffffu;
+  uint32_t sl_next = 0; /* slot of block 0 of the next polynomial: (k * NB) mod SLOTS, kept in 32 bits */
   for(size_t k = 0; k < my_polys; k++) {
     const size_t   chunk = blockIdx.x + k * gridDim.x;
     const uint32_t cp    = (uint32_t)(chunk & (((size_t)1 << s1) - 1)); /* chunk index inside its polynomial */
@@ -318,14 +320,14 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
       __syncthreads();
     }
     const size_t   g0    = k * NB;
-    const uint32_t sl0   = (uint32_t)(g0 % SLOTS);
+    /* SLOTS = 3 * HALF: a polynomial's low and high halves each sit in HALF consecutive slots, so a block address
+     * is one of two uniform bases plus a compile-time offset */
+    const uint32_t sl0 = sl_next, sh0 = sl0 + HALF >= (uint32_t)SLOTS ? sl0 + HALF - SLOTS : sl0 + HALF;
+    sl_next            = sl0 + NB >= (uint32_t)SLOTS ? sl0 + NB - SLOTS : sl0 + NB;
     mbar_wait(bars + 8u * (uint32_t)(k % C::NBAR), (uint32_t)((k / C::NBAR) & 1));
 
     /* slot of block b of this polynomial (uniform arithmetic: one compare per block) */
-    auto blk_slot = [&](uint32_t b) -> uint32_t {
-      uint32_t s = sl0 + b;
-      return s >= (uint32_t)SLOTS ? s - SLOTS : s;
-    };
+    auto blk_slot = [&](uint32_t b) -> uint32_t { return b < (uint32_t)HALF ? sl0 + b : sh0 + (b - HALF); };
 
     /* ---------- pass A (forward first, inverse last): across blocks ---------- */
     auto pass_a = [&]() {

@@ -19,11 +19,11 @@
  * an integer (tests/test_fp64_arith_model.py replays both and the schedules below on the CPU).
  * Butterflies are X' = X + t, Y' = X - t
  * (forward) and X' = X + Y, Y' = t(X - Y) (inverse) with no range correction; every pass first folds its
- * inputs to |v| <= q/2 + 6 (v - rint(v/q)*q, 3 instructions).  For q <= 2^49 - 1024: forward, 5 stages from a
- * fold: multiplied operands stay below 3.3q < 2^51 (fp_mul's rounding trick is exact there), values below
- * 4.2q; inverse, 4 stages from a fold: sums double to 8q + 96 < 2^52, which fp_mul_wide still rounds exactly;
- * 5-stage inverse passes fold once more after their first three stages.  2^49 - 1024 < q <= 2^50 - 2048 runs a
- * second schedule with one more fold per pass (see fp_network).
+ * inputs to |v| <= q/2 + 6 (v - rint(v/q)*q, 3 instructions) unless the bounds show it is not needed.  For
+ * q <= 2^49 - 1024 the forward transform folds twice (before its middle pass and at the very end; a product
+ * needs its operand below 4q = 2^51, or 8q with fp_mul_wide); the inverse, whose sums double per stage, folds
+ * every three to four stages.  2^49 - 1024 < q <= 2^50 - 2048 runs a second, more conservative schedule.  See
+ * fp_network for the numbers.
  * The last pass folds, adds q to negatives and converts back to u64: the output is the canonical residue in
  * [0,q), bit-identical to fwd_ntt_ref_harvey / inv_ntt_ref_harvey (include/ntt_reference.h:19-31,
  * src/ntt_reference.c:33-66).
@@ -72,18 +72,22 @@ __device__ __forceinline__ double fp_mul_wide(double y, double w, double winv, c
   return __dadd_rn(d, l);
 }
 /* u64 below 2^52 -> the same integer as a double (exponent splice + one DADD) */
-__device__ __forceinline__ double fp_from_u64(uint64_t v)
+__device__ __forceinline__ double fp_from_u64(uint64_t v, double neg_bias = -4503599627370496.0)
 {
-  return __dadd_rn(__hiloint2double((int)(hi32(v) | 0x43300000u), (int)lo32(v)), -4503599627370496.0);
+  /* neg_bias = -(2^52 + k): the result is v - k, exact as long as 2^52 + k is a double (k < 2^52) */
+  return __dadd_rn(__hiloint2double((int)(hi32(v) | 0x43300000u), (int)lo32(v)), neg_bias);
 }
 /* |v| < q, integer  ->  canonical residue in [0,q) as u64.  One DADD puts v next to 1.5*2^52, where consecutive
  * integers are consecutive bit patterns; the rest (subtract the constant's bits, add q to negatives) is integer
  * work on the otherwise idle ALU pipe. */
 __device__ __forceinline__ uint64_t fp_to_u64(double v, const FpC &c, uint64_t q)
 {
-  const double   t = __dadd_rn(v, c.magic);
-  const long long r = __double_as_longlong(t) - 0x4338000000000000ll; /* = v as a signed integer */
-  return (uint64_t)(r < 0 ? r + (long long)q : r);
+  const double   t  = __dadd_rn(v, c.magic);
+  const uint32_t hi = (uint32_t)__double2hiint(t), lo = (uint32_t)__double2loint(t);
+  /* bits(t) - bits(magic) = v as a signed integer; v < 0 <=> t < magic <=> hi < 0x43380000 (magic's low word is 0),
+   * so the sign test is one 32-bit compare */
+  const uint64_t r = ((uint64_t)(hi - 0x43380000u) << 32) | lo;
+  return r + (hi < 0x43380000u ? q : 0ull);
 }
 
 __device__ __forceinline__ void fp_bfly_fwd(double &x, double &y, double2 tw, const FpC &c)
@@ -114,23 +118,39 @@ __device__ __forceinline__ void fp_bfly_fwd_wide(double &x, double &y, double2 t
  * FINAL: the inverse network ends with global stage 0, whose two products carry N^-1
  * (harvey_bkw_butterfly_final, fast_mul_operators.h:94-106).
  *
- * Range schedules (n = stages since the last fold, values in units of q):
- *   Q50 = false, q <= 2^49 - 1024 (q/2^52 < 1/8):
- *     forward  bounds 0.5 -> 1.06 -> 1.70 -> 2.41 -> 3.21 -> 4.11: no second fold, operands < 3.3q < 2^51;
+ * ROLE (forward, first schedule only): 0 = middle pass, 1 = first pass (input centred to [-2q,2q) by the
+ * conversion, no fold), 2 = last pass (no fold, the caller folds the results).
+ *
+ * Range schedules (values in units of q; product bounds from the header: plain 1/2 + y/32, wide 3/4 + y/32
+ * for q/2^52 < 1/8, and twice the y-terms for q/2^52 < 1/4):
+ *   Q50 = false, q <= 2^49 - 1024:
+ *     forward  a plain product needs its operand below 4q = 2^51, a wide one below 8q:
+ *              pass A from 2:    2 -> 2.57 -> 3.15 -> 3.75 -> 4.36 (fifth stage wide) -> 5.25
+ *              pass B from fold: 0.5 -> 1.02 -> 1.55 -> 2.10 -> 2.67 -> 3.25
+ *              pass C unfolded:  3.25 -> 3.85 -> 4.47 (wide from here) -> 5.36 -> 6.28, then the final fold;
  *     inverse  sums 0.5 -> 1 -> 2 -> 4 -> 8: differences reach 8q < 2^52 at n = 4 (wide rounding), a 5-stage
  *              pass folds again after three stages.
- *   Q50 = true, q <= 2^50 - 2048 (q/2^52 < 1/4):
+ *   Q50 = true, q <= 2^50 - 2048 (every pass folds first):
  *     forward  0.5 -> 1.13 -> 1.91 -> 2.88 -> 4.10: the operand is below 2q < 2^51 for n <= 3, below 4q < 2^52
  *              at n = 4 (wide rounding), so a 5-stage pass folds again after three stages;
  *     inverse  differences are 1, 2, 4 q at n = 1, 2, 3 (wide rounding from n = 2) and every pass folds
  *              again after three stages.
+ * tests/test_fp64_arith_model.py mirrors these schedules and checks every operand against its limit.
  */
-template <int R, bool FWD, bool FINAL, bool Q50, typename TWF>
-__device__ __forceinline__ void fp_network(double (&x)[1 << R], const FpC &c, const ntt_cuda_params_t &p, TWF twf)
+struct FpNoHook {
+  __device__ __forceinline__ void operator()() const {}
+};
+/* MIDF: called once after the second stage of a forward network (the forward kernel re-arms a ring slot there) */
+template <int R, bool FWD, bool FINAL, bool Q50, int ROLE, typename TWF, typename MIDF = FpNoHook>
+__device__ __forceinline__ void fp_network(double (&x)[1 << R], const FpC &c, const ntt_cuda_params_t &p, TWF twf,
+                                           MIDF mid = MIDF())
 {
-  constexpr int n = 1 << R;
+  constexpr int  n    = 1 << R;
+  constexpr bool lean = FWD && !Q50 && ROLE != 0; /* first / last forward pass of the first schedule: no fold */
+  if(!lean) {
 #pragma unroll
-  for(int k = 0; k < n; k++) x[k] = fp_fold(x[k], c);
+    for(int k = 0; k < n; k++) x[k] = fp_fold(x[k], c);
+  }
   if(FWD) {
 #pragma unroll
     for(int u = 0; u < R; u++) {
@@ -144,10 +164,12 @@ __device__ __forceinline__ void fp_network(double (&x)[1 << R], const FpC &c, co
         const double2 tw = twf((1 << u) - 1 + sub);
 #pragma unroll
         for(int k = 0; k < d; k++) {
-          if(Q50 && R == 4 && u == 3) fp_bfly_fwd_wide(x[sub * 2 * d + k], x[sub * 2 * d + k + d], tw, c);
+          const bool wide = Q50 ? (R == 4 && u == 3) : (ROLE == 1 ? u >= 4 : (ROLE == 2 ? u >= 2 : false));
+          if(wide) fp_bfly_fwd_wide(x[sub * 2 * d + k], x[sub * 2 * d + k + d], tw, c);
           else fp_bfly_fwd(x[sub * 2 * d + k], x[sub * 2 * d + k + d], tw, c);
         }
       }
+      if(u == 1) mid();
     }
   } else {
 #pragma unroll
@@ -220,6 +242,8 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
   const size_t   my_blocks = my_polys * NB;
   const size_t   groups    = (size_t)1 << (p.logn - 4);
   const FpC      c{p.q_fd, p.qinv_fd, NTT_FP_MAGIC};
+  /* forward input [0,4q) is centred to [-2q,2q) by the conversion itself on the first schedule (see fp_network) */
+  const double   in_bias = -(4503599627370496.0 + ((FWD && !Q50) ? 2.0 * p.q_fd : 0.0));
   const double2 *g_fd  = (const double2 *)(FWD ? p.fwd_fd : p.inv_fd);
   const double2 *g_ct  = (const double2 *)(FWD ? p.fwd_ct_fd : p.inv_ct_fd);
 
@@ -264,6 +288,7 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
     for(uint32_t g = C::BOXB * tid; g < (uint32_t)SLOTS; g += C::BOXB * T) issue_box(g);
   }
   uint32_t cached_cp = 0xffffffffu;
+  uint32_t sl_next = 0; /* slot of block 0 of the next polynomial: (k * NB) mod SLOTS, kept in 32 bits */
   for(size_t k = 0; k < my_polys; k++) {
     const size_t   chunk = blockIdx.x + k * gridDim.x;
     const uint32_t cp    = (uint32_t)(chunk & (((size_t)1 << s1) - 1));
@@ -284,7 +309,10 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
       __syncthreads();
     }
     const size_t   g0  = k * NB;
-    const uint32_t sl0 = (uint32_t)(g0 % SLOTS);
+    /* SLOTS = 3 * HALF: a polynomial's low and high halves each sit in HALF consecutive slots, so a block address
+     * is one of two uniform bases plus a compile-time offset */
+    const uint32_t sl0 = sl_next, sh0 = sl0 + HALF >= (uint32_t)SLOTS ? sl0 + HALF - SLOTS : sl0 + HALF;
+    sl_next            = sl0 + NB >= (uint32_t)SLOTS ? sl0 + NB - SLOTS : sl0 + NB;
     /* blocks g0+SLOTS .. g0+SLOTS+NB-1 get their slot only when this polynomial's blocks are stored; ask L2
      * for them now so that the late TMA loads find them on chip */
     if(tid < (uint32_t)NB) {
@@ -294,6 +322,10 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
         tma_prefetch_block_l2(&tmap, (int)((ck << (L - 4)) + (uint32_t)(g % NB) * 32u));
       }
     }
+    if(FWD && k > 0 && lane == 0) { /* deferred re-arm of the previous polynomial's second block (see below) */
+      tma_wait_read_all();
+      issue_load(g0 - NB + warp + HALF + SLOTS);
+    }
     TRACE(0);
     const uint32_t bar_lo = bars + 16u * (uint32_t)(k % C::NBAR), bar_hi = bar_lo + 8u;
     const uint32_t parity = (uint32_t)((k / C::NBAR) & 1);
@@ -301,10 +333,7 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
     if(FWD) mbar_wait(bar_hi, parity);
     TRACE(1);
 
-    auto blk_slot = [&](uint32_t b) -> uint32_t {
-      uint32_t s = sl0 + b;
-      return s >= (uint32_t)SLOTS ? s - SLOTS : s;
-    };
+    auto blk_slot = [&](uint32_t b) -> uint32_t { return b < (uint32_t)HALF ? sl0 + b : sh0 + (b - HALF); };
 
     /* pass A, forward: first pass; reads the raw u64 input from the slots, leaves doubles in place. */
     auto pass_a_fwd = [&]() {
@@ -313,8 +342,8 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
         double         x[NB];
 #pragma unroll
         for(int b = 0; b < NB; b++)
-          x[b] = fp_from_u64(*reinterpret_cast<const uint64_t *>(ring_ptr + blk_slot(b) * 4096u + off));
-        fp_network<RA, true, false, Q50>(x, c, p, [&](int t) { return tw_s[t]; });
+          x[b] = fp_from_u64(*reinterpret_cast<const uint64_t *>(ring_ptr + blk_slot(b) * 4096u + off), in_bias);
+        fp_network<RA, true, false, Q50, 1>(x, c, p, [&](int t) { return tw_s[t]; });
 #pragma unroll
         for(int b = 0; b < NB; b++)
           *reinterpret_cast<double *>(ring_ptr + blk_slot(b) * 4096u + off) = x[b];
@@ -350,7 +379,7 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
          * (|v| < q) are final */
 #pragma unroll
         for(int cidx = 0; cidx < COLS; cidx++) {
-          fp_network<RA, false, true, Q50>(x[cidx], c, p, [&](int t) { return tw_s[t]; });
+          fp_network<RA, false, true, Q50, 0>(x[cidx], c, p, [&](int t) { return tw_s[t]; });
           const uint32_t j = tid + cidx * T;
 #pragma unroll
           for(int b = 0; b < NB; b++) gout[(size_t)b * 512 + j] = fp_to_u64(x[cidx][b], c, p.q);
@@ -359,7 +388,7 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
         /* strided inverse passes follow (they accept [0,2q)): fold and hand over the canonical residue */
 #pragma unroll
         for(int cidx = 0; cidx < COLS; cidx++) {
-          fp_network<RA, false, false, Q50>(x[cidx], c, p, [&](int t) { return tw_s[t]; });
+          fp_network<RA, false, false, Q50, 0>(x[cidx], c, p, [&](int t) { return tw_s[t]; });
           const uint32_t j = tid + cidx * T;
 #pragma unroll
           for(int b = 0; b < NB; b++) gout[(size_t)b * 512 + j] = fp_to_u64(fp_fold(x[cidx][b], c), c, p.q);
@@ -377,7 +406,7 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
 #pragma unroll
       for(int kk = 0; kk < 32; kk++)
         x[kk] = *reinterpret_cast<const double *>(base + kk * 128 + ((jc ^ (uint32_t)(kk & 7)) << 4));
-      fp_network<5, FWD, false, Q50>(x, c, p, [&](int t) { return tw[t]; });
+      fp_network<5, FWD, false, Q50, 0>(x, c, p, [&](int t) { return tw[t]; });
 #pragma unroll
       for(int kk = 0; kk < 32; kk++)
         *reinterpret_cast<double *>(base + kk * 128 + ((jc ^ (uint32_t)(kk & 7)) << 4)) = x[kk];
@@ -394,13 +423,15 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
         x[2 * cc]     = FWD ? __longlong_as_double((long long)v.x) : fp_from_u64(v.x);
         x[2 * cc + 1] = FWD ? __longlong_as_double((long long)v.y) : fp_from_u64(v.y);
       }
-      if(FWD && rearm_first && lane == 0) {
-        /* the first block's store has had this block's shared-memory loads to drain: re-arm its slot now */
-        tma_wait_read_all();
-        issue_load(g0 + warp + SLOTS);
-      }
       const double2 *tw = g_ct + ((size_t)cp * NB + blk) * 32 + lane;
-      fp_network<4, FWD, false, Q50>(x, c, p, [&](int t) { return __ldg(tw + (size_t)t * groups); });
+      fp_network<4, FWD, false, Q50, 2>(x, c, p, [&](int t) { return __ldg(tw + (size_t)t * groups); }, [&]() {
+        /* the first block's store has had this block's loads and two stages of butterflies to drain: its slot is
+         * re-armed here without stalling the warp (the block it receives is needed by the next polynomial's pass A) */
+        if(FWD && rearm_first && lane == 0) {
+          tma_wait_read_all();
+          issue_load(g0 + warp + SLOTS);
+        }
+      });
 #pragma unroll
       for(int cc = 0; cc < 8; cc++) {
         ulonglong2 v;
@@ -445,11 +476,9 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
       fence_proxy_async();
       __syncwarp();
       TRACE(6);
-      if(lane == 0) {
-        store_block(warp + HALF);
-        tma_wait_read_all();
-        issue_load(g0 + warp + HALF + SLOTS);
-      }
+      /* the second block's slot is re-armed at the top of the next iteration (its new block is only needed a whole
+       * polynomial later), when the store has long drained */
+      if(lane == 0) store_block(warp + HALF);
       __syncwarp();
       TRACE(7);
     } else {

@@ -133,13 +133,18 @@ class Schedule:
             err += min(operand / (1 << 53), F(1, 4))
         return self.q * (F(1, 2) + err)
 
-    def forward(self, R, b_in):
+    def forward(self, R, b_in, role):
+        """role: 1 first pass (input centred, |v| <= 2q), 0 middle, 2 last (the caller folds afterwards)"""
         assert b_in < (1 << 53)
-        b = self.fold
+        lean = not self.q50 and role != 0
+        b = b_in if lean else self.fold
         for u in range(R):
             if self.q50 and R == 5 and u == 3:
                 b = self.fold
-            wide = self.q50 and R == 4 and u == 3
+            if self.q50:
+                wide = R == 4 and u == 3
+            else:
+                wide = u >= 4 if role == 1 else (u >= 2 if role == 2 else False)
             b = b + self.mul(b, wide)
             assert b < (1 << 53)
         return b
@@ -167,9 +172,10 @@ def test_range_schedules_stay_inside_their_limits(q, q50):
     s = Schedule(q, q50)
     for RA in (3, 4, 5):                       # L = 12, 13, 14
         # forward: input contract [0,4q); passes A (RA stages), B (5), C (4), then a fold
-        b = s.forward(RA, 4 * q)
-        b = s.forward(5, b)
-        b = s.forward(4, b)
+        b = s.forward(RA, 4 * q if q50 else 2 * q, 1)
+        b = s.forward(5, b, 0)
+        b = s.forward(4, b, 2)
+        assert b < (1 << 53)                   # what the final fold accepts
         # inverse: input contract [0,2q); passes C (4), B (5), A (RA, with or without the N^-1 stage)
         b = s.inverse(4, 2 * q, False)
         b = s.inverse(5, b, False)

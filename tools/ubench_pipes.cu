@@ -11,6 +11,8 @@
 struct P { uint64_t w, wc, q; uint32_t w0, w1, v0, v1, n0, n1; };
 template <int OP>
 __global__ void __launch_bounds__(1024) k(uint64_t* out, uint32_t seed, P p) {
+  __shared__ double sh[4096];
+  if (OP >= 24) { for (int i = threadIdx.x; i < 4096; i += blockDim.x) sh[i] = i; __syncthreads(); }
   uint32_t a[NCH], b[NCH];
   uint64_t c[NCH];
   double d[NCH];
@@ -69,6 +71,21 @@ __global__ void __launch_bounds__(1024) k(uint64_t* out, uint32_t seed, P p) {
       if (OP == 17) { float f = __uint_as_float(a[i]); asm volatile("fma.rn.f32 %0, %0, %1, %1;" : "+f"(f) : "f"(1.0001f)); a[i] = __float_as_uint(f); }
       if (OP == 18) { float f = __uint_as_float(a[i]); asm volatile("fma.rn.f32 %0, %0, %1, %1;" : "+f"(f) : "f"(1.0001f)); a[i] = __float_as_uint(f);
                       asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(b[i]) : "r"(seed), "r"(seed)); }
+      if (OP == 19 || OP == 20 || OP == 21) {  // n DFMA per LOP3: n = 2, 3, 4
+        constexpr int n = OP - 17;
+#pragma unroll
+        for (int r = 0; r < n; r++) asm volatile("fma.rn.f64 %0, %0, %1, %1;" : "+d"(d[i]) : "d"(1.0000001));
+        asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b[i]), "r"(seed));
+      }
+      if (OP == 22) asm volatile("add.rn.f64 %0, %0, %1;" : "+d"(d[i]) : "d"(1.0000001));
+      if (OP == 23) asm volatile("mul.rn.f64 %0, %0, %1;" : "+d"(d[i]) : "d"(1.0000001));
+      if (OP == 24 || OP == 25) {  // n DFMA per shared-memory load (8 bytes): n = 4, 8
+        constexpr int n = OP == 24 ? 4 : 8;
+#pragma unroll
+        for (int r = 0; r < n; r++) asm volatile("fma.rn.f64 %0, %0, %1, %1;" : "+d"(d[i]) : "d"(1.0000001));
+        double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"((threadIdx.x * 8 + i * 8192) & 0x7ff8));
+        c[i] ^= (uint64_t)__double_as_longlong(v);
+      }
     }
   }
   uint64_t s = 0;
@@ -127,5 +144,12 @@ int main() {
   run<16>("IMAD + LOP3 + DFMA (3 instr)", 3);
   run<17>("FFMA", 1);
   run<18>("FFMA + IMAD (2 instr)", 2);
+  run<19>("2 DFMA + LOP3 (3 instr)", 3);
+  run<20>("3 DFMA + LOP3 (4 instr)", 4);
+  run<21>("4 DFMA + LOP3 (5 instr)", 5);
+  run<22>("add.rn.f64 (DADD)", 1);
+  run<23>("mul.rn.f64 (DMUL)", 1);
+  run<24>("4 DFMA + LDS.64 (5+1 instr)", 6);
+  run<25>("8 DFMA + LDS.64 (9+1 instr)", 10);
   return 0;
 }
