@@ -13,6 +13,7 @@ KEYS = [
     "lts__t_sectors_srcunit_tex_op_read.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
     "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
     "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
     "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
     "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_lsu.sum.pct_of_peak_sustained_active", "sm__cycles_elapsed.max",
