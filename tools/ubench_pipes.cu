@@ -79,6 +79,16 @@ __global__ void __launch_bounds__(1024) k(uint64_t* out, uint32_t seed, P p) {
       }
       if (OP == 22) asm volatile("add.rn.f64 %0, %0, %1;" : "+d"(d[i]) : "d"(1.0000001));
       if (OP == 23) asm volatile("mul.rn.f64 %0, %0, %1;" : "+d"(d[i]) : "d"(1.0000001));
+      if (OP == 26) asm volatile("cvt.rni.f64.f64 %0, %0;" : "+d"(d[i]));
+      if (OP == 27 || OP == 28) {  // n DFMA + one f64 round-to-integer: n = 3, 7
+        constexpr int n = OP == 27 ? 3 : 7;
+#pragma unroll
+        for (int r = 0; r < n; r++) asm volatile("fma.rn.f64 %0, %0, %1, %1;" : "+d"(d[i]) : "d"(1.0000001));
+        double v; asm volatile("cvt.rni.f64.f64 %0, %1;" : "=d"(v) : "d"(d[i]));
+        c[i] ^= (uint64_t)__double_as_longlong(v);
+      }
+      if (OP == 29) { double v; asm volatile("cvt.rn.f64.u64 %0, %1;" : "=d"(v) : "l"(c[i])); c[i] = (uint64_t)__double_as_longlong(v) + i; }
+      if (OP == 30) { long long v; asm volatile("cvt.rni.s64.f64 %0, %1;" : "=l"(v) : "d"(d[i])); d[i] = __longlong_as_double(v | 0x3ff0000000000000ll); }
       if (OP == 24 || OP == 25) {  // n DFMA per shared-memory load (8 bytes): n = 4, 8
         constexpr int n = OP == 24 ? 4 : 8;
 #pragma unroll
@@ -149,7 +159,10 @@ int main() {
   run<21>("4 DFMA + LOP3 (5 instr)", 5);
   run<22>("add.rn.f64 (DADD)", 1);
   run<23>("mul.rn.f64 (DMUL)", 1);
-  run<24>("4 DFMA + LDS.64 (5+1 instr)", 6);
-  run<25>("8 DFMA + LDS.64 (9+1 instr)", 10);
+  run<26>("cvt.rni.f64.f64 (round to integer)", 1);
+  run<27>("3 DFMA + cvt.rni.f64.f64 (4 instr)", 4);
+  run<28>("7 DFMA + cvt.rni.f64.f64 (8 instr)", 8);
+  run<29>("cvt.rn.f64.u64 (+IADD)", 1);
+  run<30>("cvt.rni.s64.f64 (+LOP)", 1);
   return 0;
 }
