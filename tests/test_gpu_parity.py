@@ -471,6 +471,56 @@ def test_large_n_two_pass_split(ntt, oracle):
     plan.close()
 
 
+def _random_plan_params(oracle, rng, m, bits):
+    """A prime q = 1 (mod 2N) of the given width (searched downwards from a random start) and a primitive 2N-th root."""
+    N = 1 << m
+    lo, hi = 1 << (bits - 1), (1 << bits) - 1
+    q = int(rng.integers(lo, hi, dtype=np.uint64))
+    q -= (q - 1) % (2 * N)
+    while q > lo and not oracle.is_prime(q):
+        q -= 2 * N
+    assert q > lo
+    x = 2
+    while True:
+        psi = oracle.powmod(x, (q - 1) // (2 * N), q)
+        if oracle.powmod(psi, N, q) == q - 1:
+            return N, q, psi
+        x += 1
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_plans_against_oracle(ntt, oracle, seed):
+    """Random (N, modulus width, batch) combinations -- whatever kernel the plan picks (generic, integer ring, FP64
+    ring in both range schedules, exact, strided + ring) must agree with the oracle on inputs spanning the lazy
+    contracts, with a batch that is not a multiple of anything."""
+    rng = np.random.default_rng(1000 + seed)
+    m = int(rng.integers(1, 18))
+    bits = int(rng.integers(max(m + 2, 12), 63))
+    if seed % 4 == 0:
+        bits = int(rng.integers(47, 51))          # around the FP64 schedules' boundaries
+        m = int(rng.integers(11, 17))
+    N, q, psi = _random_plan_params(oracle, rng, m, bits)
+    t = CaseTables(oracle, m, q, psi, oracle.invmod(psi, q), oracle.invmod(N, q))
+    batch = int(rng.integers(1, 12)) if m > 12 else int(rng.integers(1, 300))
+    plan = ntt.Plan.from_psi(N, q, psi)
+    top_f = min(4 * q, 1 << 64) - 1
+    a4 = oracle.uniform(batch * N, top_f, 77 + seed).reshape(batch, N)
+    a2 = oracle.uniform(batch * N, 2 * q, 78 + seed).reshape(batch, N)
+    a4[0, :] = top_f - 1
+    a2[0, :] = 2 * q - 1
+    df, di = to_dev(a4), to_dev(a2)
+    plan.fwd(df, batch)
+    plan.inv(di, batch)
+    f, i = to_host(df), to_host(di)
+    for r in sorted({0, batch // 2, batch - 1}):
+        assert np.array_equal(f[r], oracle.fwd(a4[r], q, t.w, t.w_con)), "forward, m=%d bits=%d row %d" % (m, bits, r)
+        assert np.array_equal(i[r], oracle.inv(a2[r], q, t.n_inv, t.w_inv, t.w_inv_con)), \
+            "inverse, m=%d bits=%d row %d" % (m, bits, r)
+    plan.inv(df, batch)
+    assert np.array_equal(to_host(df), a4 % np.uint64(q)), "round trip, m=%d bits=%d" % (m, bits)
+    plan.close()
+
+
 def test_error_behaviour(ntt, oracle, case_tables):
     t = case_tables(0)
     with pytest.raises(ntt.NttError):
