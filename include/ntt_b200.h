@@ -149,6 +149,31 @@ int ntt_b200_fwd_tail_block(const ntt_b200_plan_t *plan, uint64_t *d_block, uint
                             void *stream);
 int ntt_b200_inv_tail_block(const ntt_b200_plan_t *plan, uint64_t *d_block, uint32_t log2_parts, uint32_t block,
                             void *stream);
+/*
+ * The same tail stages FUSED with the exchange over peer memory (NVLink/NVSwitch), no collective call:
+ * peer_slices[p] (p < G, host array of device pointers valid on this plan's device -- the local pointer for
+ * p == rank, CUDA-IPC mappings for the others) is rank p's slice buffer of N/G words.
+ *   ntt_b200_fwd_tail_gather   loads the G members of every butterfly group straight from the peers' slices
+ *                              (after their size-N/G forward transforms), runs the last log2_parts stages and
+ *                              writes this rank's block, fully reduced -- equals all-to-all + fwd_tail_block.
+ *   ntt_b200_inv_tail_scatter  reads this rank's block, runs the first log2_parts inverse stages and stores
+ *                              member p of every group into peer p's slice -- equals inv_tail_block + all-to-all.
+ *   ntt_b200_peer_barrier      orders the ranks on the GPU timeline (stream-ordered kernel, no host sync):
+ *                              peer_flags[k] = rank k's array of `world` uint32 flags (zeroed once), epoch grows by
+ *                              one per call; *d_timed_out (device int, zeroed) is set if a peer never arrived.
+ *                              Call it between the local transforms and the gather (forward) and between the
+ *                              scatter and the local transforms (inverse).
+ *   ntt_b200_ipc_export/open/close  CUDA IPC plumbing for buffers from ntt_b200_device_alloc (64-byte handles).
+ */
+int ntt_b200_fwd_tail_gather(const ntt_b200_plan_t *plan, uint64_t *const *peer_slices, uint64_t *d_block,
+                             uint32_t log2_parts, uint32_t rank, void *stream);
+int ntt_b200_inv_tail_scatter(const ntt_b200_plan_t *plan, uint64_t *const *peer_slices, uint64_t *d_block,
+                              uint32_t log2_parts, uint32_t rank, void *stream);
+int ntt_b200_peer_barrier(int device, void *const *peer_flags, void *my_flags, uint32_t rank, uint32_t world,
+                          uint32_t epoch, int *d_timed_out, void *stream);
+int ntt_b200_ipc_export(int device, void *d_ptr, void *handle64);
+int ntt_b200_ipc_open(int device, const void *handle64, void **d_ptr);
+int ntt_b200_ipc_close(int device, void *d_ptr);
 /* Replace the inverse transform's scaling constant N^-1 by `scale` (mod q): inv_batch then returns
  * scale * N * (true inverse).  Used by the distributed inverse, whose local size-N/G transform must scale by
  * the global N^-1. */

@@ -57,6 +57,12 @@ def _bind():
         getattr(L, f).argtypes = [C.POINTER(vp), sz, vp, sz, vp]
     for f in ("ntt_b200_fwd_tail_block", "ntt_b200_inv_tail_block"):
         getattr(L, f).argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp]
+    for f in ("ntt_b200_fwd_tail_gather", "ntt_b200_inv_tail_scatter"):
+        getattr(L, f).argtypes = [vp, C.POINTER(vp), vp, C.c_uint32, C.c_uint32, vp]
+    L.ntt_b200_peer_barrier.argtypes = [i, C.POINTER(vp), vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp]
+    L.ntt_b200_ipc_export.argtypes = [i, vp, C.c_char_p]
+    L.ntt_b200_ipc_open.argtypes = [i, C.c_char_p, C.POINTER(vp)]
+    L.ntt_b200_ipc_close.argtypes = [i, vp]
     L.ntt_b200_plan_set_inverse_scale.argtypes = [vp, u64]
     L.ntt_b200_negacyclic_mul_batch.argtypes = [vp, vp, vp, vp, sz, vp]
     L.ntt_b200_pointwise_mul_batch.argtypes = [vp, vp, vp, vp, sz, vp]
@@ -99,6 +105,8 @@ EXPORTS = [
     "ntt_b200_fwd_batch", "ntt_b200_fwd_lazy_batch", "ntt_b200_inv_batch",
     "ntt_b200_fwd_rns", "ntt_b200_inv_rns",
     "ntt_b200_fwd_tail_block", "ntt_b200_inv_tail_block", "ntt_b200_plan_set_inverse_scale",
+    "ntt_b200_fwd_tail_gather", "ntt_b200_inv_tail_scatter", "ntt_b200_peer_barrier",
+    "ntt_b200_ipc_export", "ntt_b200_ipc_open", "ntt_b200_ipc_close",
     "ntt_b200_negacyclic_mul_batch", "ntt_b200_pointwise_mul_batch",
     "ntt_b200_fwd_batch_host", "ntt_b200_inv_batch_host",
     "ntt_b200_host_alloc", "ntt_b200_host_free", "ntt_b200_device_alloc", "ntt_b200_device_free",
@@ -121,6 +129,51 @@ def device_count():
 
 def version():
     return lib.ntt_b200_version().decode()
+
+
+# ---- raw device buffers and CUDA IPC (peer-memory exchange of the distributed transform) -------------------
+
+def device_alloc(device, nbytes):
+    p = C.c_void_p()
+    _check(lib.ntt_b200_device_alloc(device, C.byref(p), nbytes), "device_alloc")
+    return p.value
+
+
+def device_free(device, ptr):
+    _check(lib.ntt_b200_device_free(device, ptr), "device_free")
+
+
+def memcpy_h2d(device, d_ptr, h_arr):
+    _check(lib.ntt_b200_memcpy_h2d(device, d_ptr, h_arr.ctypes.data, h_arr.nbytes), "memcpy_h2d")
+
+
+def memcpy_d2h(device, h_arr, d_ptr):
+    _check(lib.ntt_b200_memcpy_d2h(device, h_arr.ctypes.data, d_ptr, h_arr.nbytes), "memcpy_d2h")
+
+
+def device_sync(device):
+    _check(lib.ntt_b200_device_sync(device), "device_sync")
+
+
+def ipc_export(device, d_ptr):
+    h = C.create_string_buffer(64)
+    _check(lib.ntt_b200_ipc_export(device, d_ptr, h), "ipc_export")
+    return h.raw
+
+
+def ipc_open(device, handle):
+    p = C.c_void_p()
+    _check(lib.ntt_b200_ipc_open(device, handle, C.byref(p)), "ipc_open")
+    return p.value
+
+
+def ipc_close(device, d_ptr):
+    _check(lib.ntt_b200_ipc_close(device, d_ptr), "ipc_close")
+
+
+def peer_barrier(device, peer_flags, my_flags, rank, world, epoch, d_timed_out, stream=None):
+    _check(lib.ntt_b200_peer_barrier(device, peer_flags, my_flags, rank, world, epoch, d_timed_out,
+                                     _stream_ptr(stream)), "peer_barrier")
 
 
 def configure(key, value):
@@ -259,6 +312,15 @@ class Plan:
     def inv_tail_block(self, d_block, log2_parts, block, stream=None):
         _check(lib.ntt_b200_inv_tail_block(self._h, _ptr(d_block), log2_parts, block, _stream_ptr(stream)),
                "inv_tail_block")
+
+    # the same, fused with the exchange over peer memory: peer_slices = ctypes array of G device pointers
+    def fwd_tail_gather(self, peer_slices, d_block, log2_parts, rank, stream=None):
+        _check(lib.ntt_b200_fwd_tail_gather(self._h, peer_slices, _ptr(d_block), log2_parts, rank,
+                                            _stream_ptr(stream)), "fwd_tail_gather")
+
+    def inv_tail_scatter(self, peer_slices, d_block, log2_parts, rank, stream=None):
+        _check(lib.ntt_b200_inv_tail_scatter(self._h, peer_slices, _ptr(d_block), log2_parts, rank,
+                                             _stream_ptr(stream)), "inv_tail_scatter")
 
     def set_inverse_scale(self, scale):
         _check(lib.ntt_b200_plan_set_inverse_scale(self._h, scale), "plan_set_inverse_scale")

@@ -110,6 +110,16 @@ int ntt_cuda_forward_mul(int device, const ntt_cuda_params_t *p, uint64_t *d_a, 
 /* last `glog` stages on contiguous block `block` of a transform spread over 2^glog devices (see ntt_kernels.cu) */
 int ntt_cuda_tail(int device, const ntt_cuda_params_t *p, uint64_t *d_block, uint32_t glog, uint32_t block, int inverse,
                   void *stream);
+/* the same tail stages fused with the exchange: forward gathers group members from the peers' slices
+ * (peer_slices[p], p < 2^glog, device pointers valid on this device), inverse scatters them back */
+int ntt_cuda_tail_peer(int device, const ntt_cuda_params_t *p, uint64_t *const *peer_slices, uint64_t *d_block,
+                       uint32_t glog, uint32_t rank, int inverse, void *stream);
+/* GPU-timeline barrier over peer memory; peer_flags[k] = rank k's array of `world` uint32 flags */
+int ntt_cuda_peer_barrier(int device, void *const *peer_flags, void *my_flags, uint32_t rank, uint32_t world,
+                          uint32_t epoch, int *d_timed_out, void *stream);
+int ntt_cuda_ipc_export(int device, void *d_ptr, void *handle64);
+int ntt_cuda_ipc_open(int device, const void *handle64, void **d_ptr);
+int ntt_cuda_ipc_close(int device, void *d_ptr);
 /* c = a .* b mod q over n words; inputs < q (any q < 2^62). */
 int ntt_cuda_pointwise(int device, const ntt_cuda_params_t *p, uint64_t *d_c, const uint64_t *d_a,
                        const uint64_t *d_b, size_t n, void *stream);

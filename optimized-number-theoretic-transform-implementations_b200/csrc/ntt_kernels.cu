@@ -990,6 +990,176 @@ extern "C" int ntt_cuda_tail(int device, const ntt_cuda_params_t *p, uint64_t *d
                  : dispatch_strided_groups<true, true, 1>(device, (int)glog, *p, vbase, s0, first, n_groups, st);
 }
 
+/* ------------------------------------------------------------------------------------------------ */
+/* tail stages fused with the exchange over peer memory (NVLink)                                      */
+/* ------------------------------------------------------------------------------------------------ */
+
+/*
+ * The distributed transform's exchange step without a collective: every rank maps the other ranks' slice
+ * buffers (CUDA IPC) and the tail kernel does the all-to-all itself.  Group kk of block `rank` is the G words
+ * { slice_p[rank*piece + kk] : p = 0..G-1 } (exchange_cyclic_to_blocks in fourstep.py), so
+ *   forward:  x[p] is LOADED from peer p's slice (consecutive threads read consecutive words of the same peer:
+ *             256 contiguous bytes per warp and peer), the last g stages run in registers, the fully reduced
+ *             group is stored to this rank's block;
+ *   inverse:  the group is read from this rank's block, the first g inverse stages run, x[p] is STORED into
+ *             peer p's slice.
+ * Peer data must bypass L1 (it is written by another GPU between launches): ld/st .relaxed.sys.
+ */
+struct PeerPtrs {
+  uint64_t *p[32];
+};
+__device__ __forceinline__ uint64_t ld_sys(const uint64_t *a)
+{
+  uint64_t v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_sys(uint64_t *a, uint64_t v)
+{
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(a), "l"(v) : "memory");
+}
+
+template <int R, bool FWD, bool EXACT>
+__global__ void __launch_bounds__(256) k_tail_peer(const __grid_constant__ ntt_cuda_params_t p,
+                                                   const __grid_constant__ PeerPtrs peers, uint64_t *__restrict__ block,
+                                                   uint32_t rank, size_t piece)
+{
+  constexpr int  n  = 1 << R;
+  const uint32_t s0 = p.logn - R;
+  for(size_t kk = (size_t)blockIdx.x * blockDim.x + threadIdx.x; kk < piece; kk += (size_t)gridDim.x * blockDim.x) {
+    const size_t src = (size_t)rank * piece + kk; /* index in every slice = global group index of this block */
+    uint64_t     x[n];
+    if(FWD) {
+#pragma unroll
+      for(int k = 0; k < n; k++) x[k] = ld_sys(peers.p[k] + src);
+    } else {
+#pragma unroll
+      for(int k = 0; k < n; k++) x[k] = block[(kk << R) + k];
+    }
+    radix_network<R, FWD, EXACT>(x, p, s0, (uint32_t)src);
+#pragma unroll
+    for(int k = 0; k < n; k++) {
+      uint64_t v = x[k];
+      if(FWD) {
+        block[(kk << R) + k] = finish<EXACT>(v, p);
+      } else {
+        if(!EXACT) {
+          const Red rc{p.q, p.negq, p.red_shift, p.red_mu};
+          v = reduce_2q(v, rc);
+        }
+        st_sys(peers.p[k] + src, v);
+      }
+    }
+  }
+}
+
+template <int R, bool FWD, bool EXACT>
+static int launch_tail_peer(int device, const ntt_cuda_params_t &p, const PeerPtrs &pp, uint64_t *d_block, uint32_t rank,
+                            size_t piece, cudaStream_t st)
+{
+  size_t       grid = (piece + 255) / 256;
+  const size_t cap  = (size_t)sm_count(device) * 8;
+  if(grid > cap) grid = cap;
+  k_tail_peer<R, FWD, EXACT><<<(unsigned)grid, 256, 0, st>>>(p, pp, d_block, rank, piece);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ntt_cuda_tail_peer(int device, const ntt_cuda_params_t *p, uint64_t *const *peer_slices, uint64_t *d_block,
+                                  uint32_t glog, uint32_t rank, int inverse, void *stream)
+{
+  DevGuard g(device);
+  if(!g.ok) return fail_msg("cudaSetDevice failed");
+  if(glog < 1 || glog > 5 || 2 * glog > p->logn || rank >= (1u << glog)) return fail_msg("bad tail geometry");
+  PeerPtrs pp{};
+  for(uint32_t k = 0; k < (1u << glog); k++) {
+    if(!peer_slices[k]) return fail_msg("peer slice pointer is NULL");
+    pp.p[k] = peer_slices[k];
+  }
+  const size_t piece = (size_t)1 << (p->logn - 2 * glog);
+  cudaStream_t st    = (cudaStream_t)stream;
+#define TAILPEER(R)                                                                                                   \
+  case R:                                                                                                             \
+    if(p->lazy)                                                                                                       \
+      return inverse ? launch_tail_peer<R, false, false>(device, *p, pp, d_block, rank, piece, st)                    \
+                     : launch_tail_peer<R, true, false>(device, *p, pp, d_block, rank, piece, st);                    \
+    return inverse ? launch_tail_peer<R, false, true>(device, *p, pp, d_block, rank, piece, st)                       \
+                   : launch_tail_peer<R, true, true>(device, *p, pp, d_block, rank, piece, st);
+  switch(glog) {
+    TAILPEER(1)
+    TAILPEER(2)
+    TAILPEER(3)
+    TAILPEER(4)
+    TAILPEER(5)
+  }
+#undef TAILPEER
+  return fail_msg("unsupported tail radix");
+}
+
+/*
+ * Barrier between the ranks of a distributed transform, on the GPU timeline: thread k stores `epoch` into slot
+ * `rank` of peer k's flag array (after a system-scope fence, so everything earlier kernels of this stream wrote is
+ * visible to the peer before the flag is), then waits until slot k of its own array has reached `epoch`.  Flags
+ * only grow.  The wait is bounded (about two seconds of clock64) and reports a timeout instead of hanging the GPU.
+ */
+__global__ void k_peer_barrier(const __grid_constant__ PeerPtrs flags, uint32_t rank, uint32_t world, uint32_t epoch,
+                               uint32_t *my_flags, int *timed_out)
+{
+  const uint32_t k = threadIdx.x;
+  if(k >= world) return;
+  __threadfence_system();
+  uint32_t *remote = reinterpret_cast<uint32_t *>(flags.p[k]) + rank;
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(epoch) : "memory");
+  const long long t0 = clock64();
+  uint32_t        v;
+  do {
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(my_flags + k) : "memory");
+    if((int)(v - epoch) >= 0) break;
+    __nanosleep(64);
+  } while(clock64() - t0 < 4000000000ll);
+  if((int)(v - epoch) < 0) *timed_out = 1;
+  __threadfence_system();
+}
+
+extern "C" int ntt_cuda_peer_barrier(int device, void *const *peer_flags, void *my_flags, uint32_t rank, uint32_t world,
+                                     uint32_t epoch, int *d_timed_out, void *stream)
+{
+  DevGuard g(device);
+  if(!g.ok) return fail_msg("cudaSetDevice failed");
+  if(world < 1 || world > 32 || rank >= world) return fail_msg("bad peer barrier geometry");
+  PeerPtrs pp{};
+  for(uint32_t k = 0; k < world; k++) pp.p[k] = (uint64_t *)peer_flags[k];
+  k_peer_barrier<<<1, 32, 0, (cudaStream_t)stream>>>(pp, rank, world, epoch, (uint32_t *)my_flags, d_timed_out);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+/* CUDA IPC: export a cudaMalloc'ed buffer / map a peer's buffer into this process (64-byte opaque handle). */
+extern "C" int ntt_cuda_ipc_export(int device, void *d_ptr, void *handle64)
+{
+  DevGuard g(device);
+  if(!g.ok) return fail_msg("cudaSetDevice failed");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  CU(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)handle64, d_ptr));
+  return 0;
+}
+extern "C" int ntt_cuda_ipc_open(int device, const void *handle64, void **d_ptr)
+{
+  DevGuard g(device);
+  if(!g.ok) return fail_msg("cudaSetDevice failed");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  CU(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+extern "C" int ntt_cuda_ipc_close(int device, void *d_ptr)
+{
+  DevGuard g(device);
+  if(!g.ok) return fail_msg("cudaSetDevice failed");
+  CU(cudaIpcCloseMemHandle(d_ptr));
+  return 0;
+}
+
 /*
  * RNS batch: limb l (its own modulus and tables, plist[l]) transforms `batch_per_limb` polynomials at
  * d_a + l * batch_per_limb * N.  One launch per limb would leave each CTA one or two chunks, nothing to pipeline

@@ -108,6 +108,97 @@ class DistributedNtt:
             self.full.close()
 
 
+class PeerExchange:
+    """The exchange step without a collective: every rank's slice buffer (cudaMalloc, N/G words) is mapped into
+    every other rank's address space through CUDA IPC, so the tail kernels load / store the group members straight
+    from / into peer memory over NVLink (ntt_b200_fwd_tail_gather, ntt_b200_inv_tail_scatter), and the ranks are
+    ordered by a flag barrier that runs as a kernel on the caller's stream (ntt_b200_peer_barrier).
+    `dist` is only used once, to hand the IPC handles round."""
+
+    def __init__(self, n_local, rank, world, device, dist, group=None):
+        import ctypes as C
+        self.rank, self.world, self.device, self.n_local = rank, world, device, n_local
+        self.slice_ptr = _pkg.device_alloc(device, n_local * 8)
+        self.flags_ptr = _pkg.device_alloc(device, 512)            # `world` uint32 flags, timeout word at +256
+        _pkg.memcpy_h2d(device, self.flags_ptr, np.zeros(64, dtype=np.uint64))
+        _pkg.device_sync(device)
+        mine = (_pkg.ipc_export(device, self.slice_ptr), _pkg.ipc_export(device, self.flags_ptr))
+        handles = [None] * world
+        dist.all_gather_object(handles, mine, group=group)
+        self._opened = []
+        self.slices = (C.c_void_p * world)()
+        self.flags = (C.c_void_p * world)()
+        for p in range(world):
+            if p == rank:
+                self.slices[p], self.flags[p] = self.slice_ptr, self.flags_ptr
+            else:
+                sp, fp = _pkg.ipc_open(device, handles[p][0]), _pkg.ipc_open(device, handles[p][1])
+                self._opened += [sp, fp]
+                self.slices[p], self.flags[p] = sp, fp
+        self.epoch = 0
+        self._dist, self._group = dist, group
+        dist.barrier(group=group)                                  # every rank's flags are zeroed and mapped
+
+    def barrier(self, stream=None):
+        """All ranks' work enqueued before this call (on their streams) is complete and visible afterwards."""
+        self.epoch += 1
+        _pkg.peer_barrier(self.device, self.flags, self.flags_ptr, self.rank, self.world, self.epoch,
+                          self.flags_ptr + 256, stream)
+
+    def timed_out(self):
+        w = np.zeros(1, dtype=np.uint64)
+        _pkg.memcpy_d2h(self.device, w, self.flags_ptr + 256)
+        return bool(w[0] & 0xFFFFFFFF)
+
+    def load_slice(self, host_u64):
+        assert host_u64.size == self.n_local
+        _pkg.memcpy_h2d(self.device, self.slice_ptr, np.ascontiguousarray(host_u64, dtype=np.uint64))
+
+    def read_slice(self):
+        out = np.empty(self.n_local, dtype=np.uint64)
+        _pkg.memcpy_d2h(self.device, out, self.slice_ptr)
+        return out
+
+    def close(self):
+        _pkg.device_sync(self.device)
+        self._dist.barrier(group=self._group)                      # nobody is still reading our buffers
+        for ptr in self._opened:
+            _pkg.ipc_close(self.device, ptr)
+        self._dist.barrier(group=self._group)
+        _pkg.device_free(self.device, self.slice_ptr)
+        _pkg.device_free(self.device, self.flags_ptr)
+
+
+class FusedDistributedNtt(DistributedNtt):
+    """DistributedNtt whose exchange is fused into the tail kernels (peer loads / stores, no NCCL on the data path).
+
+    The rank's cyclic slice lives in `self.px.slice_ptr` (px.load_slice / px.read_slice move it from / to the host).
+    forward(block) : slice -> this rank's block of the transform;  inverse(block) : block -> slice.
+    Calls must alternate forward / inverse (each barrier then also fences the previous step's peer accesses);
+    to repeat the same direction, call self.px.barrier() in between."""
+
+    def __init__(self, N, q, psi, rank, world, device, dist, group=None):
+        super().__init__(N, q, psi, rank, world, device)
+        assert world > 1
+        self.device = device
+        self.px = PeerExchange(self.n_local, rank, world, device, dist, group)
+
+    def forward(self, block_dev, stream=None):
+        self.local.fwd(self.px.slice_ptr, 1, stream)
+        self.px.barrier(stream)
+        self.full.fwd_tail_gather(self.px.slices, block_dev, self.g, self.rank, stream)
+        return block_dev
+
+    def inverse(self, block_dev, stream=None):
+        self.full.inv_tail_scatter(self.px.slices, block_dev, self.g, self.rank, stream)
+        self.px.barrier(stream)
+        self.local.inv(self.px.slice_ptr, 1, stream)
+
+    def close(self):
+        self.px.close()
+        super().close()
+
+
 def emulate_forward_single_gpu(N, q, psi, a_host, world):
     """All `world` ranks emulated one after the other on ONE GPU (no collective): the same kernels and the same
     index arithmetic as the multi-process path; used by the single-GPU parity test."""

@@ -398,6 +398,56 @@ int ntt_b200_inv_tail_block(const ntt_b200_plan_t *plan, uint64_t *d_block, uint
   return NTT_B200_SUCCESS;
 }
 
+int ntt_b200_fwd_tail_gather(const ntt_b200_plan_t *plan, uint64_t *const *peer_slices, uint64_t *d_block,
+                             uint32_t log2_parts, uint32_t rank, void *stream)
+{
+  if(check_batch(plan, d_block, 0)) return NTT_B200_ERROR;
+  if(!peer_slices) return set_error("peer slice table is NULL%s", NULL);
+  if(ntt_cuda_tail_peer(plan->device, &plan->params, peer_slices, d_block, log2_parts, rank, 0, stream))
+    return cuda_error("forward tail (peer gather)");
+  return NTT_B200_SUCCESS;
+}
+
+int ntt_b200_inv_tail_scatter(const ntt_b200_plan_t *plan, uint64_t *const *peer_slices, uint64_t *d_block,
+                              uint32_t log2_parts, uint32_t rank, void *stream)
+{
+  if(check_batch(plan, d_block, 1)) return NTT_B200_ERROR;
+  if(!peer_slices) return set_error("peer slice table is NULL%s", NULL);
+  if(ntt_cuda_tail_peer(plan->device, &plan->params, peer_slices, d_block, log2_parts, rank, 1, stream))
+    return cuda_error("inverse tail (peer scatter)");
+  return NTT_B200_SUCCESS;
+}
+
+int ntt_b200_peer_barrier(int device, void *const *peer_flags, void *my_flags, uint32_t rank, uint32_t world,
+                          uint32_t epoch, int *d_timed_out, void *stream)
+{
+  if(!peer_flags || !my_flags || !d_timed_out) return set_error("peer barrier: NULL argument%s", NULL);
+  if(ntt_cuda_peer_barrier(device, peer_flags, my_flags, rank, world, epoch, d_timed_out, stream))
+    return cuda_error("peer barrier");
+  return NTT_B200_SUCCESS;
+}
+
+int ntt_b200_ipc_export(int device, void *d_ptr, void *handle64)
+{
+  if(!d_ptr || !handle64) return set_error("ipc export: NULL argument%s", NULL);
+  if(ntt_cuda_ipc_export(device, d_ptr, handle64)) return cuda_error("cudaIpcGetMemHandle");
+  return NTT_B200_SUCCESS;
+}
+
+int ntt_b200_ipc_open(int device, const void *handle64, void **d_ptr)
+{
+  if(!d_ptr || !handle64) return set_error("ipc open: NULL argument%s", NULL);
+  if(ntt_cuda_ipc_open(device, handle64, d_ptr)) return cuda_error("cudaIpcOpenMemHandle");
+  return NTT_B200_SUCCESS;
+}
+
+int ntt_b200_ipc_close(int device, void *d_ptr)
+{
+  if(!d_ptr) return NTT_B200_SUCCESS;
+  if(ntt_cuda_ipc_close(device, d_ptr)) return cuda_error("cudaIpcCloseMemHandle");
+  return NTT_B200_SUCCESS;
+}
+
 int ntt_b200_fwd_batch(const ntt_b200_plan_t *plan, uint64_t *d_a, size_t batch, void *stream)
 {
   if(check_batch(plan, d_a, 0)) return NTT_B200_ERROR;

@@ -90,3 +90,96 @@ def test_distributed_transform_nccl(ntt, oracle, m):
     for r in range(world):
         back[r::world] = out[r][1]
     assert np.array_equal(back, a)
+
+
+# ---- exchange fused into the tail kernels (peer loads / stores instead of a collective) -------------------
+
+@pytest.mark.parametrize("m,world", [(16, 2), (18, 4), (20, 8), (14, 32)])
+def test_peer_gather_scatter_emulated_on_one_gpu(ntt, oracle, m, world):
+    """ntt_b200_fwd_tail_gather / ntt_b200_inv_tail_scatter with every rank's slice on the same GPU (the "peer"
+    pointers are local): same result as the reference transform, no all-to-all and no interleave copy."""
+    import ctypes as C
+    import torch
+    fourstep = importlib.import_module(PKG + ".fourstep")
+    N, q, G = 1 << m, Q49, world
+    g = G.bit_length() - 1
+    psi = _root(oracle, N, q)
+    t = CaseTables(oracle, m, q, psi, oracle.invmod(psi, q), oracle.invmod(N, q))
+    a = oracle.uniform(N, 4 * q, 6)                       # forward contract [0,4q)
+    parts = [fourstep.DistributedNtt(N, q, psi, r, G) for r in range(G)]
+    slices = [torch.from_numpy(np.ascontiguousarray(a[p::G]).view(np.int64)).cuda() for p in range(G)]
+    ptrs = (C.c_void_p * G)(*[s.data_ptr() for s in slices])
+    for p in range(G):
+        parts[p].local.fwd(slices[p], 1)
+    blocks = [torch.empty(N // G, dtype=torch.int64, device="cuda") for _ in range(G)]
+    for r in range(G):
+        parts[r].full.fwd_tail_gather(ptrs, blocks[r], g, r)
+    got = torch.cat(blocks).cpu().numpy().view(np.uint64)
+    assert np.array_equal(got, oracle.fwd(a, q, t.w, t.w_con)), "gather + tail differs from the oracle"
+    for s in slices:
+        s.fill_(-1)
+    for r in range(G):
+        parts[r].full.inv_tail_scatter(ptrs, blocks[r], g, r)
+    back = np.empty(N, dtype=np.uint64)
+    for p in range(G):
+        parts[p].local.inv(slices[p], 1)
+        back[p::G] = slices[p].cpu().numpy().view(np.uint64)
+    assert np.array_equal(back, a % np.uint64(q)), "tail + scatter + local inverse != input"
+    for d in parts:
+        d.close()
+
+
+def _peer_worker(rank, world, port, m, out):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    fourstep = importlib.import_module(PKG + ".fourstep")
+    from oracle.pyoracle import Oracle
+    orc = Oracle()
+    N, q = 1 << m, Q49
+    psi = _root(orc, N, q)
+    a = orc.uniform(N, q, 4)
+    plan = fourstep.FusedDistributedNtt(N, q, psi, rank, world, rank, dist)
+    block = torch.empty(N // world, dtype=torch.int64, device="cuda")
+    plan.px.load_slice(a[rank::world])
+    fwd_block = None
+    for it in range(3):                                   # forward / inverse pairs reuse the buffers and the flags
+        plan.forward(block)
+        if it == 0:
+            torch.cuda.synchronize()
+            fwd_block = block.cpu().numpy().view(np.uint64).copy()
+        plan.inverse(block)
+    torch.cuda.synchronize()
+    out[rank] = (fwd_block, plan.px.read_slice(), plan.px.timed_out())
+    plan.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("m", [18, 22])
+def test_distributed_transform_peer_memory(ntt, oracle, m):
+    """One process per GPU, slices mapped through CUDA IPC, GPU-side flag barrier: forward blocks equal the
+    reference transform and three forward/inverse round trips return the input."""
+    import torch
+    import torch.multiprocessing as mp
+    world = min(8, torch.cuda.device_count())
+    world = 1 << (world.bit_length() - 1)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    N, q = 1 << m, Q49
+    psi = _root(oracle, N, q)
+    t = CaseTables(oracle, m, q, psi, oracle.invmod(psi, q), oracle.invmod(N, q))
+    a = oracle.uniform(N, q, 4)
+    want = oracle.fwd(a, q, t.w, t.w_con)
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_peer_worker, args=(world, _free_port(), m, out), nprocs=world, join=True)
+    assert not any(out[r][2] for r in range(world)), "peer barrier timed out"
+    got = np.concatenate([out[r][0] for r in range(world)])
+    assert np.array_equal(got, want)
+    back = np.empty(N, dtype=np.uint64)
+    for r in range(world):
+        back[r::world] = out[r][1]
+    assert np.array_equal(back, a)

@@ -41,4 +41,24 @@ if rank == 0:
                       "single_direction_ntt_per_s": 2e3 / ms, "algorithmic_GBps": 2 * 2 * N * 8 / (ms * 1e-3) / 1e9,
                       "hbm_bound_ntt_per_s_per_gpu": 6537.3e9 / (2 * N * 8)}))
 plan.close()
-if world > 1: dist.destroy_process_group()
+if world > 1:
+    # the same pair with the exchange fused into the tail kernels (peer loads/stores over NVLink, GPU-side barrier)
+    fused = fs.FusedDistributedNtt(N, q, psi, rank, world, local, dist)
+    fused.px.load_slice(a[rank::world])
+    block = torch.empty(N // world, dtype=torch.int64, device="cuda")
+    for _ in range(3):
+        fused.forward(block); fused.inverse(block)
+    torch.cuda.synchronize()
+    assert np.array_equal(fused.px.read_slice(), a[rank::world]) and not fused.px.timed_out(), "fused round trip failed"
+    dist.barrier(); torch.cuda.synchronize(); e0.record()
+    for _ in range(steps):
+        fused.forward(block); fused.inverse(block)
+    e1.record(); torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ms = float(ms.item())
+        print(json.dumps({"config": "N=2^%d forward+inverse over %d GPU(s), exchange fused into the tail kernels (peer memory)" % (m, world),
+                          "ms_per_pair": ms, "single_direction_ntt_per_s": 2e3 / ms}))
+    fused.close()
+    dist.destroy_process_group()
