@@ -159,8 +159,10 @@ int ntt_b200_inv_tail_block(const ntt_b200_plan_t *plan, uint64_t *d_block, uint
  *   ntt_b200_inv_tail_scatter  reads this rank's block, runs the first log2_parts inverse stages and stores
  *                              member p of every group into peer p's slice -- equals inv_tail_block + all-to-all.
  *   ntt_b200_peer_barrier      orders the ranks on the GPU timeline (stream-ordered kernel, no host sync):
- *                              peer_flags[k] = rank k's array of `world` uint32 flags (zeroed once), epoch grows by
- *                              one per call; *d_timed_out (device int, zeroed) is set if a peer never arrived.
+ *                              peer_flags[k] = rank k's array of 128 uint32 (zeroed once; world <= 32 flags, the
+ *                              rest is bookkeeping); epoch grows by one per call, or pass 0 to let the device count
+ *                              the calls (the form a captured CUDA graph can replay); *d_timed_out (device int,
+ *                              zeroed) is set if a peer never arrived.
  *                              Call it between the local transforms and the gather (forward) and between the
  *                              scatter and the local transforms (inverse).
  *   ntt_b200_ipc_export/open/close  CUDA IPC plumbing for buffers from ntt_b200_device_alloc (64-byte handles).

@@ -1100,12 +1100,18 @@ extern "C" int ntt_cuda_tail_peer(int device, const ntt_cuda_params_t *p, uint64
  * Barrier between the ranks of a distributed transform, on the GPU timeline: thread k stores `epoch` into slot
  * `rank` of peer k's flag array (after a system-scope fence, so everything earlier kernels of this stream wrote is
  * visible to the peer before the flag is), then waits until slot k of its own array has reached `epoch`.  Flags
- * only grow.  The wait is bounded (about two seconds of clock64) and reports a timeout instead of hanging the GPU.
+ * only grow; the array is 128 words: flags, word 64 = timeout report, word 65 = device-side epoch counter.  The wait is bounded (about two seconds of clock64) and reports a timeout instead of hanging the GPU.
  */
 __global__ void k_peer_barrier(const __grid_constant__ PeerPtrs flags, uint32_t rank, uint32_t world, uint32_t epoch,
                                uint32_t *my_flags, int *timed_out)
 {
   const uint32_t k = threadIdx.x;
+  /* epoch == 0: count the calls on the device (word 65 of the flag array), so that a captured CUDA graph can be
+   * replayed -- every rank runs the same sequence of barriers, the counters agree */
+  __shared__ uint32_t s_epoch;
+  if(k == 0) s_epoch = epoch ? epoch : ++my_flags[65];
+  __syncthreads();
+  epoch = s_epoch;
   if(k >= world) return;
   __threadfence_system();
   uint32_t *remote = reinterpret_cast<uint32_t *>(flags.p[k]) + rank;

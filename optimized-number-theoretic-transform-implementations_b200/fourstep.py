@@ -140,9 +140,9 @@ class PeerExchange:
         dist.barrier(group=group)                                  # every rank's flags are zeroed and mapped
 
     def barrier(self, stream=None):
-        """All ranks' work enqueued before this call (on their streams) is complete and visible afterwards."""
-        self.epoch += 1
-        _pkg.peer_barrier(self.device, self.flags, self.flags_ptr, self.rank, self.world, self.epoch,
+        """All ranks' work enqueued before this call (on their streams) is complete and visible afterwards.
+        The epoch is counted on the device, so the call can be captured in a CUDA graph and replayed."""
+        _pkg.peer_barrier(self.device, self.flags, self.flags_ptr, self.rank, self.world, 0,
                           self.flags_ptr + 256, stream)
 
     def timed_out(self):
@@ -193,6 +193,19 @@ class FusedDistributedNtt(DistributedNtt):
         self.full.inv_tail_scatter(self.px.slices, block_dev, self.g, self.rank, stream)
         self.px.barrier(stream)
         self.local.inv(self.px.slice_ptr, 1, stream)
+
+    def capture_pair(self, block_dev):
+        """forward(block) followed by inverse(block) as one CUDA graph (returns the torch.cuda.CUDAGraph): the
+        pair is eight short launches, and at N = 2^22 the host's launch path is slower than the kernels."""
+        import torch
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side, capture_error_mode="relaxed"):
+            st = torch.cuda.current_stream()
+            self.forward(block_dev, st)
+            self.inverse(block_dev, st)
+        return graph
 
     def close(self):
         self.px.close()

@@ -60,5 +60,20 @@ if world > 1:
         ms = float(ms.item())
         print(json.dumps({"config": "N=2^%d forward+inverse over %d GPU(s), exchange fused into the tail kernels (peer memory)" % (m, world),
                           "ms_per_pair": ms, "single_direction_ntt_per_s": 2e3 / ms}))
+    # and the pair captured once as a CUDA graph (eight short launches: the host launch path is the bottleneck)
+    graph = fused.capture_pair(block)
+    for _ in range(3): graph.replay()
+    torch.cuda.synchronize()
+    assert np.array_equal(fused.px.read_slice(), a[rank::world]) and not fused.px.timed_out(), "graph round trip failed"
+    dist.barrier(); torch.cuda.synchronize(); e0.record()
+    for _ in range(steps): graph.replay()
+    e1.record(); torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ms = float(ms.item())
+        print(json.dumps({"config": "N=2^%d forward+inverse over %d GPU(s), fused exchange, pair replayed as a CUDA graph" % (m, world),
+                          "ms_per_pair": ms, "single_direction_ntt_per_s": 2e3 / ms}))
+    del graph
     fused.close()
     dist.destroy_process_group()
