@@ -3,7 +3,7 @@ import importlib, os, sys, numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 ntt = importlib.import_module("optimized-number-theoretic-transform-implementations_b200")
 q = 0x1FFFFFC800001
-for m, batch in ((12, 9), (13, 5), (14, 3), (15, 2), (8, 3)):
+for m, batch in ((12, 9), (13, 5), (14, 3), (15, 2), (8, 3), (14, 330), (13, 700)):  # the last two: several polynomials per CTA
     N = 1 << m
     psi = ntt.min_primitive_root(N, q) if m <= 8 else None
     if psi is None:
@@ -23,4 +23,27 @@ for m, batch in ((12, 9), (13, 5), (14, 3), (15, 2), (8, 3)):
     d2 = torch.from_numpy(a.view(np.int64)).cuda(); d3 = torch.from_numpy(a.view(np.int64)).cuda()
     plan.negacyclic_mul(d2, d2, d3, batch); torch.cuda.synchronize()
     plan.close()
+# tail stages fused with the exchange (all ranks' slices on this GPU)
+import ctypes as C
+fs = importlib.import_module("optimized-number-theoretic-transform-implementations_b200.fourstep")
+m, G = 16, 4
+N = 1 << m
+x = 2
+while True:
+    psi = ntt.pow_mod(x, (q - 1) // (2 * N), q)
+    if ntt.pow_mod(psi, N, q) == q - 1: break
+    x += 1
+a = np.random.default_rng(3).integers(0, q, size=N, dtype=np.uint64)
+parts = [fs.DistributedNtt(N, q, psi, r, G) for r in range(G)]
+slices = [torch.from_numpy(np.ascontiguousarray(a[p::G]).view(np.int64)).cuda() for p in range(G)]
+ptrs = (C.c_void_p * G)(*[t.data_ptr() for t in slices])
+blocks = [torch.empty(N // G, dtype=torch.int64, device="cuda") for _ in range(G)]
+for p in range(G): parts[p].local.fwd(slices[p], 1)
+for r in range(G): parts[r].full.fwd_tail_gather(ptrs, blocks[r], 2, r)
+for r in range(G): parts[r].full.inv_tail_scatter(ptrs, blocks[r], 2, r)
+for p in range(G): parts[p].local.inv(slices[p], 1)
+torch.cuda.synchronize()
+back = np.empty(N, dtype=np.uint64)
+for p in range(G): back[p::G] = slices[p].cpu().numpy().view(np.uint64)
+assert np.array_equal(back, a)
 print("sanitize run ok")
