@@ -5,8 +5,8 @@
  * of 512 coefficients (4 KiB).  Shared memory is a ring of SLOTS 4-KiB slots; block g of the CTA's work
  * sequence lives in slot g mod SLOTS.  Blocks arrive by TMA (cp.async.bulk.tensor, SWIZZLE_128B, one
  * mbarrier per polynomial-in-flight), results leave by TMA store straight out of the slot, and the slot is
- * re-armed with the block SLOTS positions further down the sequence.  With SLOTS = 50 at L = 14 most of the next
- * polynomial is resident before the current one finishes, so HBM traffic overlaps the
+ * re-armed with the block SLOTS positions further down the sequence.  With SLOTS = 48 at L = 14 (one and a half
+ * polynomials) half of the next polynomial is resident before the current one finishes and the rest follows block by block, so HBM traffic overlaps the
  * butterflies without any register staging.
  *
  * Forward schedule for one chunk (stage numbers local to the chunk; the inverse mirrors it):
