@@ -521,6 +521,38 @@ def test_random_plans_against_oracle(ntt, oracle, seed):
     plan.close()
 
 
+def test_plans_on_two_devices_in_one_process(ntt, oracle):
+    """The library keeps no per-process device state: plans on different GPUs can be used from one process, each on
+    its own data and stream, without disturbing the caller's current device (one process per GPU is how bench.py
+    scales, but a host application may drive several GPUs itself)."""
+    torch = _torch()
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    m, q = 14, 0x1FFFFFC800001
+    N = 1 << m
+    psi = 20456969886
+    t = CaseTables(oracle, m, q, psi, oracle.invmod(psi, q), oracle.invmod(N, q))
+    batch = 40
+    a = oracle.uniform(batch * N, q, 91).reshape(batch, N)
+    plans = [ntt.Plan.from_psi(N, q, psi, device=d) for d in (0, 1)]
+    bufs = [torch.from_numpy(np.ascontiguousarray(a).view(np.int64)).to("cuda:%d" % d) for d in (0, 1)]
+    torch.cuda.set_device(0)
+    for rnd in range(2):                       # interleave the devices
+        for d in (1, 0):
+            plans[d].fwd(bufs[d], batch)
+        assert torch.cuda.current_device() == 0
+    for d in (0, 1):
+        torch.cuda.synchronize(d)
+    want1 = oracle.fwd(a[:2], q, t.w, t.w_con)
+    want2 = oracle.fwd(want1 % np.uint64(q), q, t.w, t.w_con)
+    for d in (0, 1):
+        got = bufs[d].cpu().numpy().view(np.uint64)
+        assert np.array_equal(got[:2], want2), "device %d" % d
+    assert torch.equal(bufs[0].cpu(), bufs[1].cpu())
+    for p in plans:
+        p.close()
+
+
 def test_error_behaviour(ntt, oracle, case_tables):
     t = case_tables(0)
     with pytest.raises(ntt.NttError):
