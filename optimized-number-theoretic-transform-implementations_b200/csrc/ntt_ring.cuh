@@ -64,6 +64,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
     : "memory");
 }
 /* named barrier 1: arrive without waiting / wait for `count` threads (producer-consumer hand-off inside the CTA) */
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void named_arrive(uint32_t count) { asm volatile("bar.arrive 1, %0;" ::"r"(count) : "memory"); }
 __device__ __forceinline__ void named_sync(uint32_t count) { asm volatile("bar.sync 1, %0;" ::"r"(count) : "memory"); }
 __device__ __forceinline__ void fence_barrier_init()
@@ -125,8 +129,8 @@ struct RingCfg {
   /* the inverse re-arms a dead polynomial with four big TMA boxes of BOXB = NB/4 adjacent blocks each
    * (BOXB*32 rows <= 256): the ring depth is a multiple of BOXB so that a box never wraps */
   static constexpr int BOXB     = NB / 4;
-  static constexpr int SLOTS    = ((BUDGET - TW_BYTES - 1024 - 64) / 4096) / (NB / 2) * (NB / 2); /* 48 / 24 / 12 for L = 14 / 13 / 12 */
-  static constexpr int SMEM     = SLOTS * 4096 + 1024 /* alignment slack */ + TW_BYTES + 64 /* 8 barriers */;
+  static constexpr int SLOTS    = ((BUDGET - TW_BYTES - 1024 - 128) / 4096) / (NB / 2) * (NB / 2); /* 48 / 24 / 12 for L = 14 / 13 / 12 */
+  static constexpr int SMEM     = SLOTS * 4096 + 1024 /* alignment slack */ + TW_BYTES + 128 /* 8 load barriers + the CTA barrier */;
   static_assert(SLOTS > NB && 4 * NB > SLOTS && SLOTS % BOXB == 0, "ring depth vs. mbarrier reuse distance");
   static_assert(SLOTS % (NB / 2) == 0, "half a polynomial must not wrap around the ring (blk_slot)");
 };
