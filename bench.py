@@ -373,8 +373,11 @@ def run_b200_arm(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": workload_config(args), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, {"arithmetic": "u64 coefficients; butterflies are exact integer arithmetic "
+                                                           "carried in FP64 (q < 2^50), results bit-identical to the "
+                                                           "reference's 64-bit integer code"}),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": 2 * args.steps * world, "clocks": clocks, "impl": "b200",
         }
         print(json.dumps(line))
