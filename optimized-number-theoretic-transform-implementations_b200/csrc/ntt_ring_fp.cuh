@@ -511,15 +511,19 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
        * costs no idle time (measured at N = 2^14: inverse 0.407 -> 0.373 ms per 4096; the same reordering around a
        * plain __syncthreads gains nothing).  mbarrier because bar.arrive + bar.sync would count the warp twice.
        * PIPE_C1 is off where it measured slower (the 8- and 4-warp CTAs of L = 13 / 12). */
-      __syncwarp();
-      if(lane == 0) mbar_arrive(cta_bar);
-      if(PIPE_C1 && k + 1 < my_polys) {
-        mbar_wait(bars + 16u * (uint32_t)((k + 1) % C::NBAR), (uint32_t)(((k + 1) / C::NBAR) & 1));
-        const size_t nchunk = chunk + gridDim.x;
-        pass_c_at(sl_next + warp, warp, (uint32_t)(nchunk & (((size_t)1 << s1) - 1)), nchunk, false);
-        c1_done = true;
+      if(PIPE_C1) {
+        __syncwarp(); /* orders the other lanes' pass-B stores before lane 0's releasing arrive */
+        if(lane == 0) mbar_arrive(cta_bar);
+        if(k + 1 < my_polys) {
+          mbar_wait(bars + 16u * (uint32_t)((k + 1) % C::NBAR), (uint32_t)(((k + 1) / C::NBAR) & 1));
+          const size_t nchunk = chunk + gridDim.x;
+          pass_c_at(sl_next + warp, warp, (uint32_t)(nchunk & (((size_t)1 << s1) - 1)), nchunk, false);
+          c1_done = true;
+        }
+        mbar_wait(cta_bar, (uint32_t)(k & 1)); /* acquire: every lane waits itself */
+      } else {
+        __syncthreads();
       }
-      mbar_wait(cta_bar, (uint32_t)(k & 1));
       TRACE(5);
       pass_a_inv();
       TRACE(7);
