@@ -33,7 +33,8 @@ extern "C" {
 #define NTT_B200_MIN_LOGN 1
 #define NTT_B200_MAX_LOGN 24
 
-typedef struct ntt_b200_plan ntt_b200_plan_t; /* opaque; one per (device, N, q, psi) */
+typedef struct ntt_b200_plan  ntt_b200_plan_t;  /* opaque; one per (device, N, q, psi) */
+typedef struct ntt_b200_multi ntt_b200_multi_t; /* opaque; one plan per device of a device list */
 
 /* ---- library ------------------------------------------------------------------------------------ */
 
@@ -101,8 +102,10 @@ int ntt_b200_plan_export_tables(const ntt_b200_plan_t *plan, uint64_t *w, uint64
  * 16-byte aligned.  stream: a cudaStream_t passed as void* (NULL = default stream).  Asynchronous.
  *
  * fwd_batch      = fwd_ntt_ref_harvey      on each polynomial (include/ntt_reference.h:19-31): out in [0,q)
- * fwd_lazy_batch = fwd_ntt_ref_harvey_lazy (src/ntt_reference.c:11-31): contract is "out in [0,4q)";
- *                  this implementation returns the fully reduced representative, which satisfies it
+ * fwd_lazy_batch = fwd_ntt_ref_harvey_lazy (src/ntt_reference.c:11-31): contract is "out in [0,4q)", equal to
+ *                  fwd_batch after reduce_4q_to_q (tests/test_correctness.c:267-269).  The FP64 ring kernel
+ *                  (q <= 2^50-2048, N >= 2^12) skips its final sign correction and returns values in [0,2q);
+ *                  the other kernels have no cheaper lazy form and return the canonical residue.
  * inv_batch      = inv_ntt_ref_harvey      (src/ntt_reference.c:33-66): out in [0,q)
  */
 int ntt_b200_fwd_batch(const ntt_b200_plan_t *plan, uint64_t *d_a, size_t batch, void *stream);
@@ -129,6 +132,16 @@ int ntt_b200_negacyclic_mul_batch(const ntt_b200_plan_t *plan, uint64_t *d_c, ui
 /* c[i] = a[i]*b[i] mod q over batch*N words (NTT-domain product); inputs in [0,q). */
 int ntt_b200_pointwise_mul_batch(const ntt_b200_plan_t *plan, uint64_t *d_c, const uint64_t *d_a,
                                  const uint64_t *d_b, size_t batch, void *stream);
+/*
+ * a[b] <- INTT( NTT(a[b]) .* m ) for every polynomial b of the batch: the product of a batch with ONE fixed
+ * polynomial given in the NTT domain (d_m: N canonical residues on the plan's device; NULL = no product, a plain
+ * forward+inverse round trip).  The forward transform, the product and the inverse run back to back on `stream`
+ * (the product is fused into the forward kernel where the FP64 ring kernel serves the plan).  Composition of
+ * fwd_ntt_ref_harvey (include/ntt_reference.h:19-31), a pointwise product and inv_ntt_ref_harvey
+ * (src/ntt_reference.c:33-66).
+ */
+int ntt_b200_fwd_mul_inv_batch(const ntt_b200_plan_t *plan, uint64_t *d_a, const uint64_t *d_m, size_t batch,
+                               void *stream);
 
 /* ---- one transform spread over several GPUs (SURVEY.md section 8e, N = 2^22 config) ----------------------- */
 
@@ -189,6 +202,43 @@ int ntt_b200_plan_set_inverse_scale(ntt_b200_plan_t *plan, uint64_t scale);
  */
 int ntt_b200_fwd_batch_host(const ntt_b200_plan_t *plan, uint64_t *h_a, size_t batch);
 int ntt_b200_inv_batch_host(const ntt_b200_plan_t *plan, uint64_t *h_a, size_t batch);
+/* ntt_b200_fwd_mul_inv_batch on host memory: every chunk crosses PCIe once in each direction for a forward AND
+ * an inverse transform (d_m stays on the device; NULL = plain round trip). */
+int ntt_b200_fwd_mul_inv_batch_host(const ntt_b200_plan_t *plan, uint64_t *h_a, const uint64_t *d_m, size_t batch);
+
+/* ---- several GPUs of one node: batch / RNS-limb sharding, no collective ----- */
+
+/*
+ * One plan per device of `devices[0..n_devices)` (NULL = devices 0..n_devices-1), all for the same (N, q, psi);
+ * tables are generated on each device.  Polynomials are independent transforms (src/ntt_reference.c:11-66 works on
+ * one array), so device i owns the contiguous shard ntt_b200_shard_range(batch, n_devices, i) of a batch.
+ */
+int ntt_b200_multi_create(ntt_b200_multi_t **multi, const int *devices, int n_devices, uint64_t N, uint64_t q,
+                          uint64_t psi);
+int ntt_b200_multi_destroy(ntt_b200_multi_t *multi);
+int ntt_b200_multi_devices(const ntt_b200_multi_t *multi);
+const ntt_b200_plan_t *ntt_b200_multi_plan(const ntt_b200_multi_t *multi, int index);
+const char *           ntt_b200_multi_last_error(void);
+/* first unit and unit count of part `index` when `batch` units are split into `parts` contiguous shards */
+void ntt_b200_shard_range(size_t batch, int parts, int index, size_t *first, size_t *count);
+/* device-resident: d_a[i] = batch[i] polynomials on device i; streams[i] may be NULL (or streams NULL).
+ * Asynchronous: the launches are issued device after device from the calling thread. */
+int ntt_b200_multi_fwd_batch(const ntt_b200_multi_t *multi, uint64_t *const *d_a, const size_t *batch,
+                             void *const *streams);
+int ntt_b200_multi_inv_batch(const ntt_b200_multi_t *multi, uint64_t *const *d_a, const size_t *batch,
+                             void *const *streams);
+int ntt_b200_multi_sync(const ntt_b200_multi_t *multi);
+/* host-resident: h_a = `batch` polynomials; one host thread per device runs that device's copy/compute pipeline
+ * on its contiguous shard.  Synchronous.  d_m[i] (or d_m NULL): the multiplier's copy on device i. */
+int ntt_b200_multi_fwd_batch_host(const ntt_b200_multi_t *multi, uint64_t *h_a, size_t batch);
+int ntt_b200_multi_inv_batch_host(const ntt_b200_multi_t *multi, uint64_t *h_a, size_t batch);
+int ntt_b200_multi_fwd_mul_inv_batch_host(const ntt_b200_multi_t *multi, uint64_t *h_a, const uint64_t *const *d_m,
+                                          size_t batch);
+/* RNS limbs sharded over devices: plans[l] may live on any device and d_limb[l] points to limb l's
+ * batch_per_limb polynomials on THAT device (BASELINE config 3: 48 limbs over 2/4/8 GPUs).  Asynchronous on each
+ * device's default stream; follow with ntt_b200_device_sync per device. */
+int ntt_b200_fwd_rns_multi(ntt_b200_plan_t *const *plans, size_t limbs, uint64_t *const *d_limb, size_t batch_per_limb);
+int ntt_b200_inv_rns_multi(ntt_b200_plan_t *const *plans, size_t limbs, uint64_t *const *d_limb, size_t batch_per_limb);
 
 /* Pinned host memory helpers (cudaHostAlloc / cudaFreeHost) so C callers need no CUDA headers. */
 int ntt_b200_host_alloc(void **ptr, size_t bytes);

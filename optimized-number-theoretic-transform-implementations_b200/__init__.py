@@ -30,7 +30,8 @@ class NttError(RuntimeError):
 
 def build(verbose=False):
     """Compile libntt_b200.so / libntt_b200_dropin.so in-tree (nvcc -gencode arch=compute_100a,code=sm_100a)."""
-    subprocess.run(["make", "-C", _HERE, "all"], check=True, stdout=None if verbose else subprocess.DEVNULL)
+    subprocess.run(["make", "-j%d" % (os.cpu_count() or 4), "-C", _HERE, "all"], check=True,
+                   stdout=None if verbose else subprocess.DEVNULL)
 
 
 def _bind():
@@ -68,6 +69,24 @@ def _bind():
     L.ntt_b200_pointwise_mul_batch.argtypes = [vp, vp, vp, vp, sz, vp]
     for f in ("ntt_b200_fwd_batch_host", "ntt_b200_inv_batch_host"):
         getattr(L, f).argtypes = [vp, vp, sz]
+    L.ntt_b200_fwd_mul_inv_batch.argtypes = [vp, vp, vp, sz, vp]
+    L.ntt_b200_fwd_mul_inv_batch_host.argtypes = [vp, vp, vp, sz]
+    L.ntt_b200_multi_create.argtypes = [C.POINTER(vp), C.POINTER(i), i, u64, u64, u64]
+    L.ntt_b200_multi_destroy.argtypes = [vp]
+    L.ntt_b200_multi_devices.argtypes = [vp]
+    L.ntt_b200_multi_plan.restype = vp
+    L.ntt_b200_multi_plan.argtypes = [vp, i]
+    L.ntt_b200_multi_last_error.restype = C.c_char_p
+    L.ntt_b200_shard_range.restype = None
+    L.ntt_b200_shard_range.argtypes = [sz, i, i, C.POINTER(sz), C.POINTER(sz)]
+    for f in ("ntt_b200_multi_fwd_batch", "ntt_b200_multi_inv_batch"):
+        getattr(L, f).argtypes = [vp, C.POINTER(vp), C.POINTER(sz), C.POINTER(vp)]
+    L.ntt_b200_multi_sync.argtypes = [vp]
+    for f in ("ntt_b200_multi_fwd_batch_host", "ntt_b200_multi_inv_batch_host"):
+        getattr(L, f).argtypes = [vp, vp, sz]
+    L.ntt_b200_multi_fwd_mul_inv_batch_host.argtypes = [vp, vp, C.POINTER(vp), sz]
+    for f in ("ntt_b200_fwd_rns_multi", "ntt_b200_inv_rns_multi"):
+        getattr(L, f).argtypes = [C.POINTER(vp), sz, C.POINTER(vp), sz]
     L.ntt_b200_host_alloc.argtypes = [C.POINTER(vp), sz]
     L.ntt_b200_host_free.argtypes = [vp]
     L.ntt_b200_device_alloc.argtypes = [i, C.POINTER(vp), sz]
@@ -109,6 +128,12 @@ EXPORTS = [
     "ntt_b200_ipc_export", "ntt_b200_ipc_open", "ntt_b200_ipc_close",
     "ntt_b200_negacyclic_mul_batch", "ntt_b200_pointwise_mul_batch",
     "ntt_b200_fwd_batch_host", "ntt_b200_inv_batch_host",
+    "ntt_b200_fwd_mul_inv_batch", "ntt_b200_fwd_mul_inv_batch_host",
+    "ntt_b200_multi_create", "ntt_b200_multi_destroy", "ntt_b200_multi_devices", "ntt_b200_multi_plan",
+    "ntt_b200_multi_last_error", "ntt_b200_shard_range",
+    "ntt_b200_multi_fwd_batch", "ntt_b200_multi_inv_batch", "ntt_b200_multi_sync",
+    "ntt_b200_multi_fwd_batch_host", "ntt_b200_multi_inv_batch_host", "ntt_b200_multi_fwd_mul_inv_batch_host",
+    "ntt_b200_fwd_rns_multi", "ntt_b200_inv_rns_multi",
     "ntt_b200_host_alloc", "ntt_b200_host_free", "ntt_b200_device_alloc", "ntt_b200_device_free",
     "ntt_b200_memcpy_h2d", "ntt_b200_memcpy_d2h", "ntt_b200_device_sync",
     "ntt_b200_fwd_ntt_ref_harvey_lazy", "ntt_b200_fwd_ntt_ref_harvey", "ntt_b200_inv_ntt_ref_harvey",
@@ -331,6 +356,75 @@ class Plan:
 
     def inv_host(self, h_a, batch):
         _check(lib.ntt_b200_inv_batch_host(self._h, _ptr(h_a), batch), "inv_batch_host")
+
+    # a[b] <- INTT(NTT(a[b]) .* m): d_m = N canonical residues on the device (None: plain round trip)
+    def fwd_mul_inv(self, d_a, d_m, batch, stream=None):
+        _check(lib.ntt_b200_fwd_mul_inv_batch(self._h, _ptr(d_a), _ptr(d_m), batch, _stream_ptr(stream)),
+               "fwd_mul_inv_batch")
+
+    def fwd_mul_inv_host(self, h_a, d_m, batch):
+        _check(lib.ntt_b200_fwd_mul_inv_batch_host(self._h, _ptr(h_a), _ptr(d_m), batch), "fwd_mul_inv_batch_host")
+
+
+class MultiPlan:
+    """One plan per device of a device list (ntt_b200_multi_*): the batch is sharded contiguously, no collective."""
+
+    def __init__(self, N, q, psi, devices):
+        devs = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        if lib.ntt_b200_multi_create(C.byref(h), devs, len(devices), N, q, psi) != 0:
+            raise NttError("multi_create: %s" % lib.ntt_b200_multi_last_error().decode())
+        self._h, self.N, self.q, self.devices = h, N, q, list(devices)
+
+    def _chk(self, rc, what):
+        if rc != 0:
+            raise NttError("%s: %s" % (what, lib.ntt_b200_multi_last_error().decode()))
+
+    def close(self):
+        if self._h:
+            lib.ntt_b200_multi_destroy(self._h)
+            self._h = None
+
+    def shard(self, batch, index):
+        f, c = C.c_size_t(), C.c_size_t()
+        lib.ntt_b200_shard_range(batch, len(self.devices), index, C.byref(f), C.byref(c))
+        return int(f.value), int(c.value)
+
+    def _lists(self, d_a, batch, streams):
+        n = len(self.devices)
+        pa = (C.c_void_p * n)(*[_ptr(x) for x in d_a])
+        pb = (C.c_size_t * n)(*batch)
+        ps = (C.c_void_p * n)(*[_stream_ptr(s) for s in (streams or [None] * n)])
+        return pa, pb, ps
+
+    def fwd(self, d_a, batch, streams=None):
+        self._chk(lib.ntt_b200_multi_fwd_batch(self._h, *self._lists(d_a, batch, streams)), "multi_fwd_batch")
+
+    def inv(self, d_a, batch, streams=None):
+        self._chk(lib.ntt_b200_multi_inv_batch(self._h, *self._lists(d_a, batch, streams)), "multi_inv_batch")
+
+    def sync(self):
+        self._chk(lib.ntt_b200_multi_sync(self._h), "multi_sync")
+
+    def fwd_host(self, h_a, batch):
+        self._chk(lib.ntt_b200_multi_fwd_batch_host(self._h, _ptr(h_a), batch), "multi_fwd_batch_host")
+
+    def inv_host(self, h_a, batch):
+        self._chk(lib.ntt_b200_multi_inv_batch_host(self._h, _ptr(h_a), batch), "multi_inv_batch_host")
+
+    def fwd_mul_inv_host(self, h_a, d_m, batch):
+        pm = None if d_m is None else (C.c_void_p * len(self.devices))(*[_ptr(x) for x in d_m])
+        self._chk(lib.ntt_b200_multi_fwd_mul_inv_batch_host(self._h, _ptr(h_a), pm, batch), "multi_fwd_mul_inv_host")
+
+
+def rns_multi(plans, d_limbs, batch_per_limb, inverse=False):
+    """Limbs sharded over devices: plans[l] on any device, d_limbs[l] that limb's polynomials on the same device."""
+    n = len(plans)
+    arr = (C.c_void_p * n)(*[p._h for p in plans])
+    ptr = (C.c_void_p * n)(*[_ptr(x) for x in d_limbs])
+    fn = lib.ntt_b200_inv_rns_multi if inverse else lib.ntt_b200_fwd_rns_multi
+    if fn(arr, n, ptr, batch_per_limb) != 0:
+        raise NttError("rns_multi: %s" % lib.ntt_b200_multi_last_error().decode())
 
 
 def fwd_rns(plans, d_a, batch_per_limb, stream=None):

@@ -104,6 +104,17 @@ int ntt_cuda_inverse(int device, const ntt_cuda_params_t *p, uint64_t *d_a, size
 /* RNS batch: limb l uses *plist[l] on d_a + l*batch_per_limb*N; limbs run concurrently on internal streams */
 int ntt_cuda_rns(int device, const ntt_cuda_params_t *const *plist, size_t limbs, uint64_t *d_a, size_t batch_per_limb,
                  int inverse, void *stream);
+/* Options of the forward transform (FP64 ring kernel; other kernels ignore them and report *fused_out = 0):
+ *   d_other         multiply the transform pointwise by this array of canonical residues before it is stored
+ *   other_broadcast 0: d_other holds one operand per polynomial (batch*N words); 1: ONE polynomial (N words)
+ *   lazy_out        1: the output may stay in [0,2q) (skips the final sign correction); ignored with d_other */
+typedef struct ntt_cuda_fwd_opts {
+  const uint64_t *d_other;
+  int             other_broadcast;
+  int             lazy_out;
+} ntt_cuda_fwd_opts_t;
+int ntt_cuda_forward_ex(int device, const ntt_cuda_params_t *p, uint64_t *d_a, size_t batch, void *stream,
+                        const ntt_cuda_fwd_opts_t *opts, int *fused_out);
 /* forward transform of d_a followed by d_a .*= d_other; *fused_out says whether the kernel did the product */
 int ntt_cuda_forward_mul(int device, const ntt_cuda_params_t *p, uint64_t *d_a, const uint64_t *d_other, size_t batch,
                          void *stream, int *fused_out);
@@ -123,6 +134,10 @@ int ntt_cuda_ipc_close(int device, void *d_ptr);
 /* c = a .* b mod q over n words; inputs < q (any q < 2^62). */
 int ntt_cuda_pointwise(int device, const ntt_cuda_params_t *p, uint64_t *d_c, const uint64_t *d_a,
                        const uint64_t *d_b, size_t n, void *stream);
+
+/* c[i] = a[i] * b[i mod N] mod q: ONE polynomial b against every polynomial of a (n = batch*N words) */
+int ntt_cuda_pointwise_bcast(int device, const ntt_cuda_params_t *p, uint64_t *d_c, const uint64_t *d_a,
+                             const uint64_t *d_b, size_t n, void *stream);
 
 #ifdef __cplusplus
 }

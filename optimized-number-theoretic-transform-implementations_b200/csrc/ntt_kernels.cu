@@ -27,10 +27,11 @@
 
 #include <cstdlib>
 
+#include <mutex>
+
 #include "ntt_cuda.h"
 #include "ntt_device.cuh"
-#include "ntt_ring.cuh"
-#include "ntt_ring_fp.cuh"
+#include "ntt_launch.h"
 
 using namespace nttb200;
 
@@ -57,6 +58,10 @@ static int fail_msg(const char *what)
   } while(0)
 
 extern "C" const char *ntt_cuda_error(void) { return g_err; }
+namespace nttb200 {
+int nl_fail(const char *what, cudaError_t e) { return fail(what, e); }
+int nl_fail_msg(const char *what) { return fail_msg(what); }
+}  // namespace nttb200
 
 extern "C" int ntt_cuda_device_count(void)
 {
@@ -378,11 +383,13 @@ __global__ void k_build_tables(const uint64_t *__restrict__ d_w, uint4 *__restri
 }
 
 /* c = a .* b mod q, exact for any q < 2^62 and inputs < 2^64 (128-bit product, Barrett by 2^128/q) */
-__global__ void k_pointwise(uint64_t *__restrict__ c, const uint64_t *__restrict__ a,
-                            const uint64_t *__restrict__ b, size_t n, uint64_t q, uint64_t mu_hi, uint64_t mu_lo)
+/* no __restrict__: callers alias c with a and/or b (in-place products, squaring).  b_mask: all ones, or N-1 to
+ * broadcast ONE polynomial b over the batch. */
+__global__ void k_pointwise(uint64_t *c, const uint64_t *a, const uint64_t *b, size_t n, size_t b_mask, uint64_t q,
+                            uint64_t mu_hi, uint64_t mu_lo)
 {
   for(size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const uint64_t x = a[i], y = b[i];
+    const uint64_t x = a[i], y = b[i & b_mask];
     const uint64_t ph = mulhi64(x, y), pl = x * y;
     /* Q = floor(P * mu / 2^128) with mu = floor(2^128 / q) = mu_hi*2^64 + mu_lo; error <= 2 */
     const uint64_t t1 = mulhi64(pl, mu_hi);
@@ -427,6 +434,10 @@ static int sm_count(int device)
   }
   return cache[device];
 }
+
+namespace nttb200 {
+int nl_sm_count(int device) { return sm_count(device); }
+}  // namespace nttb200
 
 extern "C" int ntt_cuda_malloc(int device, void **d_ptr, size_t bytes)
 {
@@ -612,10 +623,28 @@ static tmap_encode_fn tmap_encoder()
   return fn;
 }
 
-/* The coefficient array seen as rows of 128 bytes (32 x u32); one TMA box = 32 rows = one 512-coefficient
- * block, written to shared memory with the 128-byte swizzle the passes are laid out for. */
+/* The coefficient array seen as rows of 128 bytes (32 x u32); one TMA box = `rows` rows (32 rows = one
+ * 512-coefficient block), written to shared memory with the 128-byte swizzle the passes are laid out for.
+ * cuTensorMapEncodeTiled costs about 10 us per call, which shows when a config launches many small batches (48 RNS
+ * limbs of 32 polynomials: 96 encodes per transform), so the last few descriptors are kept per thread, keyed on
+ * (pointer, words, rows) -- the descriptor depends on nothing else. */
 static int make_block_tmap(CUtensorMap *tm, uint64_t *d_a, size_t total_words, unsigned rows = 32)
 {
+  struct Entry {
+    uint64_t *  ptr;
+    size_t      words;
+    unsigned    rows;
+    CUtensorMap tm;
+  };
+  constexpr int                NCACHE = 128;
+  static thread_local Entry    cache[NCACHE];
+  static thread_local unsigned next = 0, used = 0;
+  for(unsigned i = 0; i < used; i++) {
+    if(cache[i].ptr == d_a && cache[i].words == total_words && cache[i].rows == rows) {
+      *tm = cache[i].tm;
+      return 0;
+    }
+  }
   tmap_encode_fn enc = tmap_encoder();
   if(!enc) return fail_msg("cuTensorMapEncodeTiled not available from the driver");
   const cuuint64_t dims[2]    = {32, (cuuint64_t)(total_words / 16)};
@@ -629,8 +658,17 @@ static int make_block_tmap(CUtensorMap *tm, uint64_t *d_a, size_t total_words, u
     snprintf(g_err, sizeof(g_err), "cuTensorMapEncodeTiled failed (%d)", (int)r);
     return -1;
   }
+  cache[next] = Entry{d_a, total_words, rows, *tm};
+  next        = (next + 1) % NCACHE;
+  if(used < NCACHE) used++;
   return 0;
 }
+namespace nttb200 {
+int nl_make_block_tmap(CUtensorMap *tm, uint64_t *d_a, size_t total_words, unsigned rows)
+{
+  return make_block_tmap(tm, d_a, total_words, rows);
+}
+}  // namespace nttb200
 
 /* kernel-selection switches (benchmarks and A/B parity tests): environment at first use, or ntt_cuda_configure */
 static int g_ring_on = -1, g_fp64_on = -1;
@@ -666,74 +704,33 @@ static bool use_fp64(const ntt_cuda_params_t &p, bool fwd)
 /* Several small launches run side by side (RNS limbs on their own streams): each then takes only as many CTAs
  * as gives every CTA a few chunks to pipeline, and leaves the other SMs to its neighbours.  0 = whole GPU. */
 static thread_local size_t g_min_chunks_per_cta = 0;
+namespace nttb200 {
+size_t nl_min_chunks_per_cta() { return g_min_chunks_per_cta; }
+}  // namespace nttb200
 
-template <int L, bool FWD, bool FP>
-static int launch_ring(int device, const ntt_cuda_params_t &p, uint64_t *d_a, size_t n_chunks, cudaStream_t st,
-                       const uint64_t *d_other = nullptr)
-{
-  using C = RingCfg<L>;
-  CUtensorMap tm, tm2;
-  if(make_block_tmap(&tm, d_a, n_chunks << L)) return -1;
-  if(FP && make_block_tmap(&tm2, d_a, n_chunks << L, 32 * C::BOXB)) return -1; /* BOXB blocks per box */
-  size_t grid = (size_t)sm_count(device) * C::CTAS;
-  if(grid > n_chunks) grid = n_chunks;
-  if(g_min_chunks_per_cta && grid * g_min_chunks_per_cta > n_chunks) {
-    grid = (n_chunks + g_min_chunks_per_cta - 1) / g_min_chunks_per_cta;
-  }
-  const bool q50 = p.fp64 == 2; /* 50-bit range schedule */
-#define NTT_LAUNCH_FP(MULV, Q50V)                                                                    \
-  do {                                                                                               \
-    auto        kern = k_ring_fp<L, FWD, MULV, Q50V>;                                                \
-    static bool ready[64] = {false};                                                                 \
-    if(!ready[device & 63]) {                                                                        \
-      CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));          \
-      ready[device & 63] = true;                                                                     \
-    }                                                                                                \
-    kern<<<(unsigned)grid, C::THREADS, C::SMEM, st>>>(p, tm, tm2, n_chunks, d_a, MULV ? d_other : nullptr); \
-  } while(0)
-  if(FP && FWD && d_other) {
-    if(q50) NTT_LAUNCH_FP((FWD), true);
-    else NTT_LAUNCH_FP((FWD), false);
-  } else if(FP) {
-    if(q50) NTT_LAUNCH_FP(false, true);
-    else NTT_LAUNCH_FP(false, false);
-#undef NTT_LAUNCH_FP
-  } else {
-    auto        kern = k_ring<L, FWD>;
-    static bool ready[64] = {false};
-    if(!ready[device & 63]) {
-      CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-      ready[device & 63] = true;
-    }
-    kern<<<(unsigned)grid, C::THREADS, C::SMEM, st>>>(p, tm, n_chunks, d_a);
-  }
-  CU(cudaGetLastError());
-  return 0;
-}
-
-/* true if the ring kernel handled the chunk stage (lazy path, chunk of 2^12..2^14, pass-C tables present) */
+/* true if the ring kernel handled the chunk stage (lazy path, chunk of 2^12..2^14, pass-C tables present).
+ * `o` (forward only): fused pointwise product / lazy output, honoured by the FP64 kernel only -- if they are asked
+ * for and the FP64 kernel cannot run, nothing is launched and *done stays false. */
 template <bool FWD>
 static int try_ring(int device, int L, const ntt_cuda_params_t &p, uint64_t *d_a, size_t n_chunks, cudaStream_t st,
-                    bool *done, const uint64_t *d_other = nullptr)
+                    bool *done, const RingOpts *o = nullptr)
 {
   *done = false;
   if(!ring_enabled() || !p.lazy || L < 12 || L > 14) return 0;
   if(!(FWD ? p.fwd_ct_wu : p.inv_ct_wu)) return 0;
   if(((uintptr_t)d_a & 127) != 0) return 0; /* TMA wants 128-byte aligned rows (cudaMalloc gives 256) */
-  if(d_other && !use_fp64(p, FWD)) return 0; /* the fused product exists on the FP64 kernel only */
+  if(o && o->d_other && !use_fp64(p, FWD)) return 0; /* the fused product exists on the FP64 kernel only */
   *done = true;
   if(use_fp64(p, FWD)) {
+    const RingOpts none;
+    const RingOpts &ro = o ? *o : none;
     switch(L) {
-      case 12: return launch_ring<12, FWD, true>(device, p, d_a, n_chunks, st, d_other);
-      case 13: return launch_ring<13, FWD, true>(device, p, d_a, n_chunks, st, d_other);
-      default: return launch_ring<14, FWD, true>(device, p, d_a, n_chunks, st, d_other);
+      case 12: return ring_fp_launch_12(FWD, device, p, d_a, n_chunks, st, ro);
+      case 13: return ring_fp_launch_13(FWD, device, p, d_a, n_chunks, st, ro);
+      default: return ring_fp_launch_14(FWD, device, p, d_a, n_chunks, st, ro);
     }
   }
-  switch(L) {
-    case 12: return launch_ring<12, FWD, false>(device, p, d_a, n_chunks, st);
-    case 13: return launch_ring<13, FWD, false>(device, p, d_a, n_chunks, st);
-    default: return launch_ring<14, FWD, false>(device, p, d_a, n_chunks, st);
-  }
+  return ring_int_launch(L, FWD, device, p, d_a, n_chunks, st);
 }
 
 /* ---- transform dispatch ---------------------------------------------------------------------------- */
@@ -881,7 +878,7 @@ extern "C" int ntt_cuda_plan_inverse_bounds(ntt_cuda_params_t *p)
  * whether that happened (it does on the FP64 ring kernel), otherwise nothing was multiplied. */
 template <bool EXACT>
 static int forward_impl(int device, const ntt_cuda_params_t &p, uint64_t *d_a, size_t batch, cudaStream_t st,
-                        const uint64_t *d_other = nullptr, bool *fused = nullptr)
+                        const ntt_cuda_fwd_opts_t *opts = nullptr, bool *fused = nullptr)
 {
   if(fused) *fused = false;
   const Split sp = make_split((int)p.logn);
@@ -896,8 +893,12 @@ static int forward_impl(int device, const ntt_cuda_params_t &p, uint64_t *d_a, s
   }
   if(!EXACT) {
     bool done = false;
-    if(d_other) {
-      if(try_ring<true>(device, sp.L, p, d_a, batch << s0, st, &done, d_other)) return -1;
+    if(opts && (opts->d_other || opts->lazy_out)) {
+      RingOpts ro;
+      ro.d_other    = opts->d_other;
+      ro.other_mask = opts->other_broadcast ? (((size_t)1 << s0) - 1) : ~(size_t)0;
+      ro.lazy_out   = opts->lazy_out != 0 && !opts->d_other;
+      if(try_ring<true>(device, sp.L, p, d_a, batch << s0, st, &done, &ro)) return -1;
       if(done) {
         if(fused) *fused = true;
         return 0;
@@ -938,21 +939,31 @@ extern "C" int ntt_cuda_forward(int device, const ntt_cuda_params_t *p, uint64_t
                  : forward_impl<true>(device, *p, d_a, batch, (cudaStream_t)stream);
 }
 
-/* forward transform of d_a, then d_a[i] *= d_other[i] mod q; *fused_out = 1 if the product was done inside the
- * transform kernel, 0 if the caller still has to multiply (ntt_cuda_pointwise) */
-extern "C" int ntt_cuda_forward_mul(int device, const ntt_cuda_params_t *p, uint64_t *d_a, const uint64_t *d_other,
-                                    size_t batch, void *stream, int *fused_out)
+/* forward transform with options (ntt_cuda_fwd_opts_t): a pointwise product fused before the store and / or a lazy
+ * output.  *fused_out = 1 if the chunk kernel honoured them; 0 means a plain, fully reduced transform was run and
+ * the caller still has to multiply (ntt_cuda_pointwise). */
+extern "C" int ntt_cuda_forward_ex(int device, const ntt_cuda_params_t *p, uint64_t *d_a, size_t batch, void *stream,
+                                   const ntt_cuda_fwd_opts_t *opts, int *fused_out)
 {
-  *fused_out = 0;
+  if(fused_out) *fused_out = 0;
   if(batch == 0) return 0;
   DevGuard g(device);
   if(!g.ok) return fail_msg("cudaSetDevice failed");
   if(p->logn < 1 || p->logn > NTT_MAX_STAGES) return fail_msg("logn out of range");
   bool      fused = false;
-  const int rc    = p->lazy ? forward_impl<false>(device, *p, d_a, batch, (cudaStream_t)stream, d_other, &fused)
+  const int rc    = p->lazy ? forward_impl<false>(device, *p, d_a, batch, (cudaStream_t)stream, opts, &fused)
                             : forward_impl<true>(device, *p, d_a, batch, (cudaStream_t)stream);
-  *fused_out      = fused ? 1 : 0;
+  if(fused_out) *fused_out = fused ? 1 : 0;
   return rc;
+}
+
+extern "C" int ntt_cuda_forward_mul(int device, const ntt_cuda_params_t *p, uint64_t *d_a, const uint64_t *d_other,
+                                    size_t batch, void *stream, int *fused_out)
+{
+  ntt_cuda_fwd_opts_t o;
+  memset(&o, 0, sizeof(o));
+  o.d_other = d_other;
+  return ntt_cuda_forward_ex(device, p, d_a, batch, stream, &o, fused_out);
 }
 
 extern "C" int ntt_cuda_inverse(int device, const ntt_cuda_params_t *p, uint64_t *d_a, size_t batch, void *stream)
@@ -971,12 +982,40 @@ extern "C" int ntt_cuda_inverse(int device, const ntt_cuda_params_t *p, uint64_t
  * input in [0,4q), output fully reduced.  Inverse: the same stages backwards (they come first), input in
  * [0,2q), output below 2q for the complete local inverse that follows the exchange.
  */
-extern "C" int ntt_cuda_tail(int device, const ntt_cuda_params_t *p, uint64_t *d_block, uint32_t glog, uint32_t block,
+/* The inverse tail runs stages logn-1 .. logn-glog as ONE register network, whatever pass structure the size-N plan
+ * was laid out for, so the plan's inv_c[] / inv_renorm_mask (computed for that structure: a renormalisation may be
+ * scheduled at stage logn-5, which this network would skip) do not apply.  Recompute the bounds for the tail's own
+ * stages: B = 2 (input contract), then 10, 20, 40, 80; no renormalisation inside. */
+static int tail_inverse_params(const ntt_cuda_params_t *p, uint32_t glog, ntt_cuda_params_t *out)
+{
+  *out = *p;
+  if(!p->lazy) return 0;
+  long double lim = 9223372036854775808.0L / (long double)p->q;
+  if(lim > 2097152.0L) lim = 2097152.0L;
+  long double B = 2.0L;
+  uint32_t    mask = p->inv_renorm_mask;
+  for(uint32_t u = 0; u < glog; u++) {
+    const uint32_t s = p->logn - 1 - u;
+    if(2 * B >= lim) return fail_msg("q too large for the lazy inverse tail");
+    out->inv_c[s] = (uint64_t)B * p->q;
+    mask &= ~(1u << s);
+    B = (2 * B > 10.0L) ? 2 * B : 10.0L;
+  }
+  out->inv_renorm_mask = mask;
+  return 0;
+}
+
+extern "C" int ntt_cuda_tail(int device, const ntt_cuda_params_t *p_in, uint64_t *d_block, uint32_t glog, uint32_t block,
                              int inverse, void *stream)
 {
   DevGuard g(device);
   if(!g.ok) return fail_msg("cudaSetDevice failed");
-  if(glog < 1 || glog > 5 || 2 * glog > p->logn || block >= (1u << glog)) return fail_msg("bad tail geometry");
+  if(glog < 1 || glog > 5 || 2 * glog > p_in->logn || block >= (1u << glog)) return fail_msg("bad tail geometry");
+  ntt_cuda_params_t tp;
+  if(inverse) {
+    if(tail_inverse_params(p_in, glog, &tp)) return -1;
+  }
+  const ntt_cuda_params_t *p = inverse ? &tp : p_in;
   const uint32_t s0       = p->logn - glog;
   const size_t   n_groups = (size_t)1 << (p->logn - 2 * glog);       /* groups of 2^glog words in one block */
   const size_t   first    = (size_t)block * n_groups;
@@ -1065,12 +1104,17 @@ static int launch_tail_peer(int device, const ntt_cuda_params_t &p, const PeerPt
   return 0;
 }
 
-extern "C" int ntt_cuda_tail_peer(int device, const ntt_cuda_params_t *p, uint64_t *const *peer_slices, uint64_t *d_block,
-                                  uint32_t glog, uint32_t rank, int inverse, void *stream)
+extern "C" int ntt_cuda_tail_peer(int device, const ntt_cuda_params_t *p_in, uint64_t *const *peer_slices,
+                                  uint64_t *d_block, uint32_t glog, uint32_t rank, int inverse, void *stream)
 {
   DevGuard g(device);
   if(!g.ok) return fail_msg("cudaSetDevice failed");
-  if(glog < 1 || glog > 5 || 2 * glog > p->logn || rank >= (1u << glog)) return fail_msg("bad tail geometry");
+  if(glog < 1 || glog > 5 || 2 * glog > p_in->logn || rank >= (1u << glog)) return fail_msg("bad tail geometry");
+  ntt_cuda_params_t tp;
+  if(inverse) {
+    if(tail_inverse_params(p_in, glog, &tp)) return -1;
+  }
+  const ntt_cuda_params_t *p = inverse ? &tp : p_in;
   PeerPtrs pp{};
   for(uint32_t k = 0; k < (1u << glog); k++) {
     if(!peer_slices[k]) return fail_msg("peer slice pointer is NULL");
@@ -1216,8 +1260,8 @@ extern "C" int ntt_cuda_rns(int device, const ntt_cuda_params_t *const *plist, s
   return rc;
 }
 
-extern "C" int ntt_cuda_pointwise(int device, const ntt_cuda_params_t *p, uint64_t *d_c, const uint64_t *d_a,
-                                  const uint64_t *d_b, size_t n, void *stream)
+static int pointwise_launch(int device, const ntt_cuda_params_t *p, uint64_t *d_c, const uint64_t *d_a,
+                           const uint64_t *d_b, size_t n, size_t b_mask, void *stream)
 {
   if(n == 0) return 0;
   DevGuard g(device);
@@ -1229,17 +1273,20 @@ extern "C" int ntt_cuda_pointwise(int device, const ntt_cuda_params_t *p, uint64
   size_t         grid  = (n + 255) / 256;
   const size_t   cap   = (size_t)sm_count(device) * 16;
   if(grid > cap) grid = cap;
-  k_pointwise<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(d_c, d_a, d_b, n, p->q, mu_hi, mu_lo);
+  k_pointwise<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(d_c, d_a, d_b, n, b_mask, p->q, mu_hi, mu_lo);
   CU(cudaGetLastError());
   return 0;
 }
 
-
-#ifdef NTT_RING_TRACE
-extern "C" int ntt_cuda_trace_read(long long *out, size_t n)
+extern "C" int ntt_cuda_pointwise(int device, const ntt_cuda_params_t *p, uint64_t *d_c, const uint64_t *d_a,
+                                  const uint64_t *d_b, size_t n, void *stream)
 {
-  cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(out, nttb200::g_trace, n * sizeof(long long));
-  return 0;
+  return pointwise_launch(device, p, d_c, d_a, d_b, n, ~(size_t)0, stream);
 }
-#endif
+
+/* c[i] = a[i] * b[i mod N] mod q: one polynomial b (N = 2^logn words) against every polynomial of the batch */
+extern "C" int ntt_cuda_pointwise_bcast(int device, const ntt_cuda_params_t *p, uint64_t *d_c, const uint64_t *d_a,
+                                        const uint64_t *d_b, size_t n, void *stream)
+{
+  return pointwise_launch(device, p, d_c, d_a, d_b, n, ((size_t)1 << p->logn) - 1, stream);
+}

@@ -1,0 +1,51 @@
+/*
+ * csrc/ntt_launch.h -- internal glue between the translation units of the CUDA layer.
+ *
+ * ntt_kernels.cu holds the dispatch logic, the generic kernels and the helpers below; the ring kernels are
+ * instantiated in their own translation units (ntt_ring_fp_{12,13,14}.cu, ntt_ring_int.cu) so that the library
+ * builds in parallel.  Not part of the C-ABI.
+ */
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+
+#include "ntt_cuda.h"
+
+namespace nttb200 {
+
+int nl_fail(const char *what, cudaError_t e);
+int nl_fail_msg(const char *what);
+int nl_sm_count(int device);
+/* the coefficient array as rows of 128 bytes, one TMA box = `rows` rows, SWIZZLE_128B (cached per pointer/size) */
+int nl_make_block_tmap(CUtensorMap *tm, uint64_t *d_a, size_t total_words, unsigned rows);
+/* several small launches side by side (RNS limbs): chunks every CTA should at least get; 0 = use the whole GPU */
+size_t nl_min_chunks_per_cta();
+
+/* what the forward ring kernel may be asked to do on top of the transform */
+struct RingOpts {
+  const uint64_t *d_other    = nullptr; /* multiply pointwise by this transform-domain array before storing */
+  size_t          other_mask = ~(size_t)0; /* chunk index mask into d_other: all ones = one operand per polynomial,
+                                              2^(logn-L)-1 = ONE polynomial broadcast over the batch */
+  bool            lazy_out   = false;   /* output may stay in [0,2q) (no final sign correction) */
+};
+
+/* one launcher per translation unit; `fwd` selects the direction */
+int ring_fp_launch_12(bool fwd, int device, const ntt_cuda_params_t &p, uint64_t *d_a, size_t n_chunks, cudaStream_t st,
+                      const RingOpts &o);
+int ring_fp_launch_13(bool fwd, int device, const ntt_cuda_params_t &p, uint64_t *d_a, size_t n_chunks, cudaStream_t st,
+                      const RingOpts &o);
+int ring_fp_launch_14(bool fwd, int device, const ntt_cuda_params_t &p, uint64_t *d_a, size_t n_chunks, cudaStream_t st,
+                      const RingOpts &o);
+int ring_int_launch(int L, bool fwd, int device, const ntt_cuda_params_t &p, uint64_t *d_a, size_t n_chunks,
+                    cudaStream_t st);
+
+}  // namespace nttb200
+
+#define NL_CU(call)                                             \
+  do {                                                          \
+    cudaError_t e_ = (call);                                    \
+    if(e_ != cudaSuccess) return nttb200::nl_fail(#call, e_);   \
+  } while(0)

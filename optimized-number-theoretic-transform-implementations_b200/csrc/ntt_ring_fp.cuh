@@ -90,6 +90,14 @@ __device__ __forceinline__ uint64_t fp_to_u64(double v, const FpC &c, uint64_t q
   return r + (hi < 0x43380000u ? q : 0ull);
 }
 
+/* |v| < q, integer -> v + q in (0, 2q) as u64: the lazy representative, no sign test (bias = 1.5*2^52 + q) */
+__device__ __forceinline__ uint64_t fp_to_u64_lazy(double v, double bias)
+{
+  const double   t  = __dadd_rn(v, bias);
+  const uint32_t hi = (uint32_t)__double2hiint(t), lo = (uint32_t)__double2loint(t);
+  return ((uint64_t)(hi - 0x43380000u) << 32) | lo;
+}
+
 __device__ __forceinline__ void fp_bfly_fwd(double &x, double &y, double2 tw, const FpC &c)
 {
   const double t = fp_mul(y, tw.x, tw.y, c);
@@ -218,16 +226,23 @@ __device__ long long g_trace[16 * 64 * 8]; /* [warp][poly][event] for CTA 0 */
 #define TRACE(ev)
 #endif
 
-/* MUL (forward only): multiply the transform pointwise by `p_other` (another transform of the same shape,
- * canonical residues) before it is written -- the NTT-domain product of a negacyclic polynomial multiply, fused
- * into the second forward transform.  p_out: the array itself (the inverse writes its results directly). */
-template <int L, bool FWD, bool MUL = false, bool Q50 = false>
+/* MODE (forward only):
+ *   RING_MUL   multiply the transform pointwise by `p_other` (a transform of the same shape, canonical residues;
+ *              chunk c of this array meets chunk (c & other_mask) of p_other, so one polynomial can be broadcast
+ *              over the batch) before it is written -- the NTT-domain product of a negacyclic polynomial multiply,
+ *              fused into the second forward transform;
+ *   RING_LAZY  leave the output in [0,2q) like fwd_ntt_ref_harvey_lazy leaves it in [0,4q) (src/ntt_reference.c:11-31):
+ *              the last fold is kept (the values must fit the window) but the sign correction is not.
+ * p_out: the array itself (the inverse writes its results directly). */
+enum { RING_PLAIN = 0, RING_MUL = 1, RING_LAZY = 2 };
+template <int L, bool FWD, int MODE = RING_PLAIN, bool Q50 = false>
 __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
   k_ring_fp(const __grid_constant__ ntt_cuda_params_t p, const __grid_constant__ CUtensorMap tmap,
             const __grid_constant__ CUtensorMap tmap2, size_t n_chunks, uint64_t *__restrict__ p_out,
-            const uint64_t *__restrict__ p_other)
+            const uint64_t *__restrict__ p_other, size_t other_mask)
 {
-  static_assert(FWD || !MUL, "the fused product belongs to the forward kernel");
+  constexpr bool MUL = MODE == RING_MUL, LAZY = MODE == RING_LAZY;
+  static_assert(FWD || MODE == RING_PLAIN, "the fused product and the lazy output belong to the forward kernel");
   using C = RingCfg<L>;
   constexpr int NB = C::NB, RA = C::RA, SLOTS = C::SLOTS, T = C::THREADS, HALF = NB / 2;
 #ifndef NTT_PIPE_C1_MINL
@@ -249,6 +264,7 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
   const FpC      c{p.q_fd, p.qinv_fd, NTT_FP_MAGIC};
   /* forward input [0,4q) is centred to [-2q,2q) by the conversion itself on the first schedule (see fp_network) */
   const double   in_bias = -(4503599627370496.0 + ((FWD && !Q50) ? 2.0 * p.q_fd : 0.0));
+  const double   q_bias = NTT_FP_MAGIC + p.q_fd; /* lazy output: v + q lands in (0, 2q) */
   const double2 *g_fd  = (const double2 *)(FWD ? p.fwd_fd : p.inv_fd);
   const double2 *g_ct  = (const double2 *)(FWD ? p.fwd_ct_fd : p.inv_ct_fd);
 
@@ -448,10 +464,13 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
           /* other operand: same position of the other transform; o/q is rounded on the fly (it only steers the
            * quotient estimate).  The product of a folded value with a residue below q is below 0.51q. */
           const ulonglong2 o = __ldg(reinterpret_cast<const ulonglong2 *>(
-            p_other + (chunk << L) + (size_t)blk * 512 + lane * 16 + 2 * cc));
+            p_other + ((chunk & other_mask) << L) + (size_t)blk * 512 + lane * 16 + 2 * cc));
           const double o0 = fp_from_u64(o.x), o1 = fp_from_u64(o.y);
           v.x = fp_to_u64(fp_mul(fp_fold(x[2 * cc], c), o0, __dmul_rn(o0, c.qinv), c), c, p.q);
           v.y = fp_to_u64(fp_mul(fp_fold(x[2 * cc + 1], c), o1, __dmul_rn(o1, c.qinv), c), c, p.q);
+        } else if(FWD && LAZY) {
+          v.x = fp_to_u64_lazy(fp_fold(x[2 * cc], c), q_bias);
+          v.y = fp_to_u64_lazy(fp_fold(x[2 * cc + 1], c), q_bias);
         } else if(FWD) {
           v.x = fp_to_u64(fp_fold(x[2 * cc], c), c, p.q);
           v.y = fp_to_u64(fp_fold(x[2 * cc + 1], c), c, p.q);

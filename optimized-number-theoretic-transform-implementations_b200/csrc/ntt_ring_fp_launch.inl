@@ -1,0 +1,66 @@
+/* csrc/ntt_ring_fp_launch.inl -- body shared by ntt_ring_fp_{12,13,14}.cu; NTT_RING_L selects the chunk size. */
+#include "ntt_launch.h"
+#include "ntt_ring_fp.cuh"
+
+namespace nttb200 {
+
+template <int L, bool FWD, int MODE, bool Q50>
+static int ring_fp_launch_one(int device, const ntt_cuda_params_t &p, const CUtensorMap &tm, const CUtensorMap &tm2,
+                              unsigned grid, uint64_t *d_a, size_t n_chunks, cudaStream_t st, const RingOpts &o)
+{
+  using C               = RingCfg<L>;
+  auto        kern      = k_ring_fp<L, FWD, MODE, Q50>;
+  static bool ready[64] = {false};
+  if(!ready[device & 63]) {
+    NL_CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    ready[device & 63] = true;
+  }
+  kern<<<grid, C::THREADS, C::SMEM, st>>>(p, tm, tm2, n_chunks, d_a, o.d_other, o.other_mask);
+  NL_CU(cudaGetLastError());
+  return 0;
+}
+
+#define NTT_RING_CAT2(a, b) a##b
+#define NTT_RING_CAT(a, b) NTT_RING_CAT2(a, b)
+
+int NTT_RING_CAT(ring_fp_launch_, NTT_RING_L)(bool fwd, int device, const ntt_cuda_params_t &p, uint64_t *d_a,
+                                              size_t n_chunks, cudaStream_t st, const RingOpts &o)
+{
+  constexpr int L = NTT_RING_L;
+  using C         = RingCfg<L>;
+  CUtensorMap tm, tm2;
+  if(nl_make_block_tmap(&tm, d_a, n_chunks << L, 32)) return -1;
+  if(nl_make_block_tmap(&tm2, d_a, n_chunks << L, 32 * C::BOXB)) return -1; /* BOXB blocks per box */
+  size_t grid = (size_t)nl_sm_count(device) * C::CTAS;
+  if(grid > n_chunks) grid = n_chunks;
+  const size_t mc = nl_min_chunks_per_cta();
+  if(mc && grid * mc > n_chunks) grid = (n_chunks + mc - 1) / mc;
+  const bool     q50 = p.fp64 == 2; /* 50-bit range schedule */
+  const unsigned g   = (unsigned)grid;
+  if(!fwd) {
+    return q50 ? ring_fp_launch_one<L, false, RING_PLAIN, true>(device, p, tm, tm2, g, d_a, n_chunks, st, o)
+               : ring_fp_launch_one<L, false, RING_PLAIN, false>(device, p, tm, tm2, g, d_a, n_chunks, st, o);
+  }
+  if(o.d_other) {
+    return q50 ? ring_fp_launch_one<L, true, RING_MUL, true>(device, p, tm, tm2, g, d_a, n_chunks, st, o)
+               : ring_fp_launch_one<L, true, RING_MUL, false>(device, p, tm, tm2, g, d_a, n_chunks, st, o);
+  }
+  if(o.lazy_out) {
+    return q50 ? ring_fp_launch_one<L, true, RING_LAZY, true>(device, p, tm, tm2, g, d_a, n_chunks, st, o)
+               : ring_fp_launch_one<L, true, RING_LAZY, false>(device, p, tm, tm2, g, d_a, n_chunks, st, o);
+  }
+  return q50 ? ring_fp_launch_one<L, true, RING_PLAIN, true>(device, p, tm, tm2, g, d_a, n_chunks, st, o)
+             : ring_fp_launch_one<L, true, RING_PLAIN, false>(device, p, tm, tm2, g, d_a, n_chunks, st, o);
+}
+
+}  // namespace nttb200
+
+#if defined(NTT_RING_TRACE) && NTT_RING_L == 14
+/* -DNTT_RING_TRACE builds only: phase timestamps of CTA 0 (tools/trace_phases.py) */
+extern "C" int ntt_cuda_trace_read(long long *out, size_t n)
+{
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, nttb200::g_trace, n * sizeof(long long));
+  return 0;
+}
+#endif

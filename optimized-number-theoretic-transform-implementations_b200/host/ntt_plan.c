@@ -457,8 +457,13 @@ int ntt_b200_fwd_batch(const ntt_b200_plan_t *plan, uint64_t *d_a, size_t batch,
 
 int ntt_b200_fwd_lazy_batch(const ntt_b200_plan_t *plan, uint64_t *d_a, size_t batch, void *stream)
 {
-  /* [0,q) is a valid lazy representative of the reference's [0,4q) contract */
-  return ntt_b200_fwd_batch(plan, d_a, batch, stream);
+  /* fwd_ntt_ref_harvey_lazy (src/ntt_reference.c:11-31) leaves its output in [0,4q) and lets the caller reduce.
+   * Here the FP64 ring kernel skips its final sign correction and returns values in [0,2q); the kernels that have
+   * no cheaper lazy form return the canonical residue, which satisfies the same contract. */
+  if(check_batch(plan, d_a, 0)) return NTT_B200_ERROR;
+  ntt_cuda_fwd_opts_t o = {NULL, 0, 1};
+  if(ntt_cuda_forward_ex(plan->device, &plan->params, d_a, batch, stream, &o, NULL)) return cuda_error("forward NTT");
+  return NTT_B200_SUCCESS;
 }
 
 int ntt_b200_inv_batch(const ntt_b200_plan_t *plan, uint64_t *d_a, size_t batch, void *stream)
@@ -515,6 +520,16 @@ int ntt_b200_negacyclic_mul_batch(const ntt_b200_plan_t *plan, uint64_t *d_c, ui
                                   size_t batch, void *stream)
 {
   if(check_batch(plan, d_a, 1) || check_batch(plan, d_b, 0) || check_batch(plan, d_c, 0)) return NTT_B200_ERROR;
+  if(d_a == d_b) {
+    /* squaring: one forward transform, the NTT-domain square, the inverse (the fused second forward would read
+     * its own half-transformed buffer as the other operand) */
+    if(ntt_b200_fwd_batch(plan, d_a, batch, stream)) return NTT_B200_ERROR;
+    if(ntt_b200_pointwise_mul_batch(plan, d_a, d_a, d_a, batch, stream)) return NTT_B200_ERROR;
+    if(ntt_b200_inv_batch(plan, d_a, batch, stream)) return NTT_B200_ERROR;
+    if(d_c != d_a && ntt_cuda_d2d(plan->device, d_c, d_a, batch * (size_t)plan->N * 8, stream))
+      return cuda_error("result copy");
+    return NTT_B200_SUCCESS;
+  }
   /* the product lands in `prod` (the operand transformed second): prefer the one that aliases d_c */
   uint64_t *first = d_a, *prod = d_b;
   if(d_c == d_a) {
@@ -552,13 +567,35 @@ static int pipe_prepare(ntt_b200_plan_t *pl)
   return NTT_B200_SUCCESS;
 }
 
-/* H2D -> transform -> D2H in chunks, pipe_depth chunks in flight on their own streams */
-static int host_apply(const ntt_b200_plan_t *plan, uint64_t *h_a, size_t batch, int inverse)
+/* The three things the host-buffer pipeline can do to a chunk between its two copies */
+enum { HOST_FWD = 0, HOST_INV = 1, HOST_FWD_MUL_INV = 2 };
+
+static int host_chunk_work(const ntt_b200_plan_t *pl, uint64_t *d, size_t take, int mode, const uint64_t *d_m, void *st)
+{
+  if(mode == HOST_FWD) return ntt_cuda_forward(pl->device, &pl->params, d, take, st);
+  if(mode == HOST_INV) return ntt_cuda_inverse(pl->device, &pl->params, d, take, st);
+  /* forward, NTT-domain product with ONE resident polynomial (fused into the transform where the kernel can), inverse */
+  if(d_m) {
+    ntt_cuda_fwd_opts_t o = {d_m, 1, 0};
+    int                 fused = 0;
+    if(ntt_cuda_forward_ex(pl->device, &pl->params, d, take, st, &o, &fused)) return -1;
+    if(!fused && ntt_cuda_pointwise_bcast(pl->device, &pl->params, d, d, d_m, take * (size_t)pl->N, st)) return -1;
+  } else if(ntt_cuda_forward(pl->device, &pl->params, d, take, st)) {
+    return -1;
+  }
+  return ntt_cuda_inverse(pl->device, &pl->params, d, take, st);
+}
+
+/* H2D -> transform(s) -> D2H in chunks; chunk i runs on stream i mod depth with its own staging buffer.  Nothing
+ * waits on the host inside the loop: a slot's buffer is reused by the NEXT chunk on the SAME stream, so stream
+ * order already puts that chunk's H2D behind the previous D2H, while the copies and kernels of the other slots
+ * overlap with it (full-duplex PCIe: H2D of chunk i+1, kernels of chunk i, D2H of chunk i-1). */
+static int host_apply(const ntt_b200_plan_t *plan, uint64_t *h_a, size_t batch, int mode, const uint64_t *d_m)
 {
   if(!plan) return set_error("plan is NULL%s", NULL);
   if(!h_a) return set_error("data pointer is NULL%s", NULL);
-  if(inverse ? !plan->has_inv : !plan->has_fwd)
-    return set_error("plan was created without the %s tables", inverse ? "inverse" : "forward");
+  if((mode != HOST_INV && !plan->has_fwd) || (mode != HOST_FWD && !plan->has_inv))
+    return set_error("plan was created without the %s tables", mode == HOST_INV || plan->has_fwd ? "inverse" : "forward");
   if(batch == 0) return NTT_B200_SUCCESS;
   ntt_b200_plan_t *pl = (ntt_b200_plan_t *)plan; /* pipeline state is internal and lock-protected */
   pthread_mutex_lock(&pl->pipe_lock);
@@ -571,12 +608,8 @@ static int host_apply(const ntt_b200_plan_t *plan, uint64_t *h_a, size_t batch, 
     const size_t bytes = take * poly_words * 8;
     void *       st    = pl->pipe_stream[slot];
     uint64_t *   d     = pl->pipe_buf[slot];
-    /* the slot's previous D2H must have drained before its buffer is overwritten */
-    if(ntt_cuda_sync(pl->device, st)) rc = cuda_error("pipeline sync");
-    if(!rc && ntt_cuda_h2d(pl->device, d, h_a + done * poly_words, bytes, st)) rc = cuda_error("H2D copy");
-    if(!rc && (inverse ? ntt_cuda_inverse(pl->device, &pl->params, d, take, st)
-                       : ntt_cuda_forward(pl->device, &pl->params, d, take, st)))
-      rc = cuda_error("transform");
+    if(ntt_cuda_h2d(pl->device, d, h_a + done * poly_words, bytes, st)) rc = cuda_error("H2D copy");
+    if(!rc && host_chunk_work(pl, d, take, mode, d_m, st)) rc = cuda_error("transform");
     if(!rc && ntt_cuda_d2h(pl->device, h_a + done * poly_words, d, bytes, st)) rc = cuda_error("D2H copy");
     done += take;
     slot = (slot + 1) % pl->pipe_depth;
@@ -590,11 +623,25 @@ static int host_apply(const ntt_b200_plan_t *plan, uint64_t *h_a, size_t batch, 
 
 int ntt_b200_fwd_batch_host(const ntt_b200_plan_t *plan, uint64_t *h_a, size_t batch)
 {
-  return host_apply(plan, h_a, batch, 0);
+  return host_apply(plan, h_a, batch, HOST_FWD, NULL);
 }
 int ntt_b200_inv_batch_host(const ntt_b200_plan_t *plan, uint64_t *h_a, size_t batch)
 {
-  return host_apply(plan, h_a, batch, 1);
+  return host_apply(plan, h_a, batch, HOST_INV, NULL);
+}
+int ntt_b200_fwd_mul_inv_batch_host(const ntt_b200_plan_t *plan, uint64_t *h_a, const uint64_t *d_m, size_t batch)
+{
+  if(d_m && ((uintptr_t)d_m & 15) != 0) return set_error("device data must be 16-byte aligned%s", NULL);
+  return host_apply(plan, h_a, batch, HOST_FWD_MUL_INV, d_m);
+}
+
+int ntt_b200_fwd_mul_inv_batch(const ntt_b200_plan_t *plan, uint64_t *d_a, const uint64_t *d_m, size_t batch,
+                               void *stream)
+{
+  if(check_batch(plan, d_a, 1) || check_batch(plan, d_a, 0)) return NTT_B200_ERROR;
+  if(d_m && ((uintptr_t)d_m & 15) != 0) return set_error("device data must be 16-byte aligned%s", NULL);
+  if(host_chunk_work(plan, d_a, batch, HOST_FWD_MUL_INV, d_m, stream)) return cuda_error("forward-multiply-inverse");
+  return NTT_B200_SUCCESS;
 }
 
 int ntt_b200_host_alloc(void **ptr, size_t bytes)

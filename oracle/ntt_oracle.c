@@ -262,3 +262,64 @@ uint64_t oracle_fnv1a64(const uint64_t *a, size_t n)
   }
   return h;
 }
+
+/* ---- whole batches on several host threads (the every-row soak and bench.py's in-run check) ----------------
+ * rows x N contiguous polynomials, each transformed by oracle_fwd / oracle_inv above; `threads` pthreads take
+ * rows round-robin.  Same arithmetic, only the loop over independent polynomials is parallel. */
+#include <pthread.h>
+typedef struct {
+  uint64_t *a;
+  size_t rows, first, step;
+  uint64_t N, q, n_inv, n_inv_con;
+  const uint64_t *w, *w_con;
+  int inverse;
+} batch_job_t;
+
+static void *batch_worker(void *arg)
+{
+  const batch_job_t *j = (const batch_job_t *)arg;
+  for(size_t r = j->first; r < j->rows; r += j->step) {
+    if(j->inverse) oracle_inv(j->a + r * j->N, j->N, j->q, j->n_inv, j->n_inv_con, 64, j->w, j->w_con);
+    else oracle_fwd(j->a + r * j->N, j->N, j->q, j->w, j->w_con);
+  }
+  return NULL;
+}
+
+static void batch_run(batch_job_t base, unsigned threads)
+{
+  if(threads < 1) threads = 1;
+  if(threads > 256) threads = 256;
+  pthread_t   tid[256];
+  batch_job_t job[256];
+  unsigned    started = 0;
+  for(unsigned t = 0; t < threads; t++) {
+    job[t]       = base;
+    job[t].first = t;
+    job[t].step  = threads;
+    if(pthread_create(&tid[t], NULL, batch_worker, &job[t]) != 0) break;
+    started++;
+  }
+  if(started < threads) { /* could not start them all: finish the missing residues here */
+    for(unsigned t = started; t < threads; t++) {
+      job[t]       = base;
+      job[t].first = t;
+      job[t].step  = threads;
+      batch_worker(&job[t]);
+    }
+  }
+  for(unsigned t = 0; t < started; t++) pthread_join(tid[t], NULL);
+}
+
+void oracle_fwd_batch(uint64_t *a, size_t rows, uint64_t N, uint64_t q, const uint64_t *w, const uint64_t *w_con,
+                      unsigned threads)
+{
+  batch_job_t b = {a, rows, 0, 1, N, q, 0, 0, w, w_con, 0};
+  batch_run(b, threads);
+}
+
+void oracle_inv_batch(uint64_t *a, size_t rows, uint64_t N, uint64_t q, uint64_t n_inv, uint64_t n_inv_con,
+                      const uint64_t *w, const uint64_t *w_con, unsigned threads)
+{
+  batch_job_t b = {a, rows, 0, 1, N, q, n_inv, n_inv_con, w, w_con, 1};
+  batch_run(b, threads);
+}

@@ -48,6 +48,13 @@ void oracle_inv(uint64_t *a, uint64_t N, uint64_t q, uint64_t n_inv, uint64_t n_
 /* src/ntt_reference.c:71-91 + include/ntt_reference.h:51-65 (fwd_ntt_ref_harvey_dbl) */
 void oracle_fwd_dbl(uint64_t *a1, uint64_t *a2, uint64_t N, uint64_t q, const uint64_t *w, const uint64_t *w_con);
 
+/* oracle_fwd / oracle_inv over `rows` contiguous polynomials, rows dealt round-robin to `threads` pthreads
+ * (the arithmetic per polynomial is the single-threaded code above) */
+void oracle_fwd_batch(uint64_t *a, size_t rows, uint64_t N, uint64_t q, const uint64_t *w, const uint64_t *w_con,
+                      unsigned threads);
+void oracle_inv_batch(uint64_t *a, size_t rows, uint64_t N, uint64_t q, uint64_t n_inv, uint64_t n_inv_con,
+                      const uint64_t *w, const uint64_t *w_con, unsigned threads);
+
 /* Mathematical definition: out[i] = sum_j a[j] * psi^((2*bitrev(i)+1)*j) mod q.
  * O(N^2); an independent cross-check of the butterfly network for small N. */
 void oracle_fwd_definition(uint64_t *out, const uint64_t *a, uint64_t N, uint64_t q, uint64_t psi);

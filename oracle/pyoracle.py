@@ -48,6 +48,8 @@ class Oracle:
         L.oracle_fwd.argtypes = [_U64P, u64, u64, _U64P, _U64P]
         L.oracle_fwd_dbl.argtypes = [_U64P, _U64P, u64, u64, _U64P, _U64P]
         L.oracle_inv.argtypes = [_U64P, u64, u64, u64, u64, C.c_uint, _U64P, _U64P]
+        L.oracle_fwd_batch.argtypes = [_U64P, C.c_size_t, u64, u64, _U64P, _U64P, C.c_uint]
+        L.oracle_inv_batch.argtypes = [_U64P, C.c_size_t, u64, u64, u64, u64, _U64P, _U64P, C.c_uint]
         L.oracle_fwd_definition.argtypes = [_U64P, _U64P, u64, u64, u64]
         L.oracle_negacyclic_mul.argtypes = [_U64P, _U64P, _U64P, u64, u64]
         L.oracle_pointwise_mul.argtypes = [_U64P, _U64P, _U64P, u64, u64]
@@ -95,6 +97,22 @@ class Oracle:
         flat = out.reshape(-1, wi.shape[0])
         for row in flat:
             self.L.oracle_inv(row, row.shape[0], q, n_inv, n_inv_con, 64, wi, wic)
+        return out
+
+    def fwd_batch(self, a, q, w, wc, threads=None):
+        """oracle_fwd on every row, rows spread over host threads (same arithmetic, see ntt_oracle.c)."""
+        out = np.ascontiguousarray(a, dtype=np.uint64).copy()
+        N = w.shape[0]
+        self.L.oracle_fwd_batch(out.reshape(-1), out.size // N, N, q, w, wc, threads or os.cpu_count() or 1)
+        return out
+
+    def inv_batch(self, a, q, n_inv, wi, wic, n_inv_con=None, threads=None):
+        if n_inv_con is None:
+            n_inv_con = self.companion(n_inv, q)
+        out = np.ascontiguousarray(a, dtype=np.uint64).copy()
+        N = wi.shape[0]
+        self.L.oracle_inv_batch(out.reshape(-1), out.size // N, N, q, n_inv, n_inv_con, wi, wic,
+                                threads or os.cpu_count() or 1)
         return out
 
     def fwd_definition(self, a, q, psi):
