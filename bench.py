@@ -8,11 +8,20 @@ Workload (BASELINE.json configs[1]): batched forward+inverse NTT, N = 2^14, 49-b
 of the whole batch followed by the inverse transform of the whole batch (2 * batch single-direction NTTs
 per GPU).  The batch is 512 MiB per GPU, four times the 126 MB L2, so every step streams from HBM.
 
-Printed JSON (rank 0, one line): metric/value = whole-job single-direction NTTs per second over all GPUs,
-timed with CUDA events on the launch stream, max over ranks; `roofline` = forward chunk kernel against the
-measured HBM copy bandwidth (algorithmic bytes 2*N*8 per transform); `cpu_baseline` = the reference's own
-CPU code (oracle/_ref) on this box's host cores; `e2e` = same metric through the host-buffer C-ABI calls
-(ntt_b200_fwd_batch_host / ntt_b200_inv_batch_host) with pinned host memory, copies inside the timing.
+Printed JSON (rank 0, one line):
+  metric/value   whole-job single-direction NTTs per second over all GPUs, CUDA events on the launch stream,
+                 max over ranks (`sustained`: the same loop run for >= 2 s with its own clock record);
+  roofline       forward chunk kernel against the measured HBM copy bandwidth (algorithmic bytes 2*N*8 per
+                 transform), the inverse beside it, and `issue_bound`: the SM issue-slot roofline that actually
+                 limits the FP64 formulation (DESIGN.md section 6);
+  cpu_baseline   the reference's own CPU code (oracle/_ref) on this box's host cores (N=1 only);
+  e2e            same metric through the host-buffer C-ABI call ntt_b200_fwd_mul_inv_batch_host (every chunk
+                 crosses PCIe once per direction for a forward AND an inverse transform), pinned host memory,
+                 copies inside the timing; `separate_calls` = forward and inverse as two host calls (the round-1
+                 figure); `copy_bound` = a bare pinned H2D+D2H of the same bytes on the same box;
+  parity         >= 8 random polynomials of the timed batch compared with the oracle, outside the timed region;
+  other_configs  BASELINE configs 3 (RNS N=2^16 x 48 limbs, sharded by limb), 4 (negacyclic multiply N=2^13) and,
+                 when WORLD_SIZE > 1, 5 (one N=2^22 transform over all GPUs, exchange over NVLink).
 
 --impl reference times the reference's CPU implementation (oracle/_ref, all host threads) on the same
 config and prints the same line with "impl": "reference".
@@ -32,10 +41,11 @@ PKG = "optimized-number-theoretic-transform-implementations_b200"
 
 LOGN = 14
 Q49 = 0x1FFFFFC800001
-PSI = {13: 94912374482, 14: 20456969886, 16: 3471868370}  # smallest primitive 2N-th roots
+PSI = {13: 94912374482, 14: 20456969886, 16: 3471868370, 22: 142690821}  # smallest primitive 2N-th roots
 BATCH_PER_GPU = 4096
 METRIC = "fwd+inv NTTs/s (N=2^14, 49-bit q, batched)"
 UNIT = "NTT/s"
+PARITY_ROWS = 8
 
 
 def parse_args():
@@ -47,28 +57,45 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="polynomials per GPU")
     ap.add_argument("--logn", type=int, default=LOGN)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip other_configs, sustained and copy-bound legs")
     ap.add_argument("--cpu-seconds", type=float, default=3.0, help="target seconds per CPU baseline leg")
+    ap.add_argument("--sustain-seconds", type=float, default=2.0)
     return ap.parse_args()
 
 
-def workload_config(args, extra=None):
-    cfg = {
+def workload_config(args):
+    """Identical in both arms (the driver compares the dicts): the workload only, nothing about who runs it."""
+    return {
         "workload": "batched forward+inverse negacyclic NTT, N=2^%d, 49-bit q=%#x, batch %d per GPU "
                     "(BASELINE configs[1])" % (args.logn, Q49, args.batch),
         "N": 1 << args.logn, "q": Q49, "batch_per_gpu": args.batch,
+        "input": "splitmix64(seed = 1 + rank) %% q, uniform in [0,q)",
         "step": "forward then inverse transform of the batch; value counts single-direction transforms",
         "cache": "inputs larger than L2 (batch is %d MiB per GPU)" % ((args.batch << args.logn) * 8 >> 20),
         "parallelism": "polynomials sharded across GPUs, no data-path collective",
     }
-    if extra:
-        cfg.update(extra)
-    return cfg
 
 
 def psi_for(logn, ntt=None):
     if logn in PSI:
         return PSI[logn]
     return ntt.min_primitive_root(1 << logn, Q49)
+
+
+def splitmix64_mod(n, q, seed):
+    """a[i] = splitmix64 stream (state seed) reduced mod q -- vectorised, bit-identical
+    to oracle_fill_uniform / the generator behind the golden hashes."""
+    import numpy as np
+    out = np.empty(n, dtype=np.uint64)
+    step = 1 << 22
+    with np.errstate(over="ignore"):
+        for lo in range(0, n, step):
+            k = np.arange(lo + 1, min(n, lo + step) + 1, dtype=np.uint64)
+            z = np.uint64(seed) + k * np.uint64(0x9E3779B97F4A7C15)
+            z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+            z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+            out[lo:lo + len(k)] = (z ^ (z >> np.uint64(31))) % np.uint64(q)
+    return out
 
 
 # ---- clocks ---------------------------------------------------------------------------------------------
@@ -123,6 +150,17 @@ class ClockSampler:
         med = s[len(s) // 2] if s else None
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
                 "samples": len(s)}
+
+
+def bind_near_gpu(index):
+    """Run this process (and so allocate its pinned buffers) on the CPUs NVML reports as local to the GPU."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index))
+        return True
+    except Exception:
+        return False
 
 
 # ---- reference CPU arm ---------------------------------------------------------------------------------------
@@ -222,7 +260,8 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall * 1e3 / max(1, args.steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": workload_config(args, {"device": "host CPU, %d threads" % cpu.threads}),
+        "config": workload_config(args),
+        "arm": "reference CPU code on the host, %d threads" % cpu.threads,
         "cpu_baseline": cpu.describe(value, seconds),
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -242,29 +281,218 @@ def load_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def load_compute_bound(fwd_ntt_per_s):
-    """The arithmetic-pipe roofline of the forward kernel: measured DFMA issue rate (tools/ubench_pipes.cu) divided
-    by the FP64 instructions one transform executes; north_star's roofline is the slower of HBM and this.
-    (The integer formulation's bound, from tools/ubench_bfly.cu, is reported beside it.)"""
+def load_profile_numbers():
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-            t = json.load(fh)
-        peak = float(t["fp64_ops_per_s"]) / float(t["fp64_ops_per_fwd_ntt_logn14"])
-        return {"bound": "FP64 pipe (DFMA/DADD/DMUL issue rate)", "peak_ntt_per_s": peak,
-                "achieved_ntt_per_s": fwd_ntt_per_s, "frac": fwd_ntt_per_s / peak, "source": t.get("fp64_source"),
-                "integer_path_peak_ntt_per_s": float(t["int_pipe_bfly_per_s"]) / float(t["bfly_per_fwd_ntt_logn14"])}
+            return json.load(fh)
+    except Exception:
+        return {}
+
+
+def issue_bound(prof, fwd_ntt_per_s, sm_mhz):
+    """The roofline that actually binds the FP64 formulation: the SM issue slots.  An FP64 instruction holds a
+    scheduler's dispatch port for 2 cycles and every other instruction for 1 (tools/ubench_rf.cu,
+    profiles/r02_ubench_rf.txt), so one transform costs (2*F + O) issue cycles per warp, F and O counted from the
+    SASS of the shipped kernel (profiles/traffic.json)."""
+    try:
+        f, o = float(prof["fwd14_fp64_instr_per_thread"]), float(prof["fwd14_other_instr_per_thread"])
+        warps, scheds, sms = 16.0, 4.0, 148.0
+        cycles = (2.0 * f + o) * warps / scheds                 # per polynomial per SM
+        peak = sms * (sm_mhz or 1965) * 1e6 / cycles
+        return {"bound": "SM issue slots (2 cycles per FP64 instruction, 1 per other instruction)",
+                "fp64_instr_per_thread": f, "other_instr_per_thread": o, "peak_ntt_per_s": peak,
+                "achieved_ntt_per_s": fwd_ntt_per_s, "frac": fwd_ntt_per_s / peak,
+                "source": prof.get("issue_source")}
     except Exception:
         return None
 
 
-def load_traffic(logn):
-    """dram bytes per launch of the forward chunk kernel from the committed ncu capture, or None."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-            t = json.load(fh)
-        return t.get("fwd_logn%d_dram_bytes_per_ntt" % logn)
-    except Exception:
-        return None
+def event_pair(torch):
+    return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+
+def timed_ms(torch, fn, steps, warm=3, stream=None):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = event_pair(torch)
+    e0.record(stream)
+    for _ in range(steps):
+        fn()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def oracle_tables(orc, logn, q, psi):
+    N = 1 << logn
+    w, wc = orc.tables(N, q, psi)
+    psi_inv = orc.invmod(psi, q)
+    wi, wic = orc.tables(N, q, psi_inv)
+    return dict(w=w, wc=wc, wi=wi, wic=wic, n_inv=orc.invmod(N, q))
+
+
+def run_config3(ntt, torch, dist, rank, world, local, peak):
+    """BASELINE config 3: CKKS-style RNS batch, N = 2^16, 48 limbs (largest 49-bit primes = 1 mod 2^17), 32
+    polynomials per limb, limbs sharded contiguously over the ranks; one limb spot-checked against the oracle."""
+    import numpy as np
+    from oracle.pyoracle import Oracle
+    m, limbs, per = 16, 48, 32
+    N = 1 << m
+    qs, q = [], (1 << 49) + 1
+    q -= (q - 1) % (2 * N)
+    while len(qs) < limbs:
+        q -= 2 * N
+        if ntt.is_prime(q) and q <= (1 << 49) - 1024:
+            qs.append(q)
+    lb, le = limbs * rank // world, limbs * (rank + 1) // world
+    mine = qs[lb:le]
+    psis = [ntt.min_primitive_root(N, ql) for ql in mine]
+    plans = [ntt.Plan.from_psi(N, ql, ps, device=local) for ql, ps in zip(mine, psis)]
+    a = np.stack([splitmix64_mod(per * N, ql, 2000 + lb + i).reshape(per, N) for i, ql in enumerate(mine)])
+    d = torch.from_numpy(a.view(np.int64)).cuda()
+    ntt.fwd_rns(plans, d, per)
+    f = d.cpu().numpy().view(np.uint64)
+    orc = Oracle()
+    t = oracle_tables(orc, m, mine[0], psis[0])
+    ok = bool(np.array_equal(f[0, :2], orc.fwd_batch(a[0, :2], mine[0], t["w"], t["wc"])))
+    ntt.inv_rns(plans, d, per)
+    ok = ok and bool(np.array_equal(d.cpu().numpy().view(np.uint64), a))
+    if world > 1:
+        dist.barrier()
+    ms_f = timed_ms(torch, lambda: ntt.fwd_rns(plans, d, per), 10)
+    ms_i = timed_ms(torch, lambda: ntt.inv_rns(plans, d, per), 10)
+    if world > 1:
+        tt = torch.tensor([ms_f, ms_i, 0.0 if ok else 1.0], device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_f, ms_i, bad = tt.tolist()
+        ok = bad == 0.0
+    for p in plans:
+        p.close()
+    n = limbs * per
+    return {"config": "RNS N=2^16 x %d limbs x %d polynomials, 49-bit primes, limbs sharded over %d GPU(s)"
+                      % (limbs, per, world),
+            "fwd_ms": ms_f, "inv_ms": ms_i, "fwd_ntt_per_s": n / ms_f * 1e3, "inv_ntt_per_s": n / ms_i * 1e3,
+            "fwd_frac_of_hbm_single_pass_per_gpu": n * 2 * N * 8 / (ms_f * 1e-3) / (peak * 1e9) / world,
+            "inv_frac_of_hbm_single_pass_per_gpu": n * 2 * N * 8 / (ms_i * 1e-3) / (peak * 1e9) / world,
+            "parity_vs_oracle": ok}
+
+
+def run_config4(ntt, torch, peak):
+    """BASELINE config 4: negacyclic polynomial multiply, N = 2^13, batch 16384; rows checked against the oracle
+    pipeline (forward x2, pointwise product, inverse)."""
+    import numpy as np
+    from oracle.pyoracle import Oracle
+    m, batch, q, psi = 13, 16384, Q49, PSI[13]
+    N = 1 << m
+    plan = ntt.Plan.from_psi(N, q, psi)
+    a = splitmix64_mod(batch * N, q, 3).reshape(batch, N)
+    b = splitmix64_mod(batch * N, q, 33).reshape(batch, N)
+    da, db = torch.from_numpy(a.view(np.int64)).cuda(), torch.from_numpy(b.view(np.int64)).cuda()
+    dc = torch.empty_like(da)
+    plan.negacyclic_mul(dc, da, db, batch)
+    c = dc.cpu().numpy().view(np.uint64)
+    orc = Oracle()
+    t = oracle_tables(orc, m, q, psi)
+    rows = [0, 1, 4097, 9999, batch - 1]
+    fa, fb = orc.fwd_batch(a[rows], q, t["w"], t["wc"]), orc.fwd_batch(b[rows], q, t["w"], t["wc"])
+    want = orc.inv_batch(orc.pointwise_mul(fa, fb, q).reshape(len(rows), N), q, t["n_inv"], t["wi"], t["wic"])
+    ok = bool(np.array_equal(c[rows], want))
+    da.copy_(torch.from_numpy(a.view(np.int64)))
+    db.copy_(torch.from_numpy(b.view(np.int64)))
+    ms = timed_ms(torch, lambda: plan.negacyclic_mul(da, da, db, batch), 10)   # in place: db is work space
+    plan.close()
+    return {"config": "negacyclic polynomial multiply N=2^13, batch %d" % batch, "ms": ms,
+            "products_per_s": batch / ms * 1e3, "frac_of_hbm_3N8": batch * 3 * N * 8 / (ms * 1e-3) / (peak * 1e9),
+            "parity_vs_oracle": ok}
+
+
+def run_config5(ntt, torch, dist, rank, world, local):
+    """BASELINE config 5: ONE forward+inverse NTT of size N = 2^22 spread over all ranks -- the only path with a real
+    exchange.  Two variants: NCCL all-to-all between the local transforms and the tail stages, and the exchange
+    fused into the tail kernels over NVLink peer memory (CUDA IPC, GPU-side flag barrier).  Rank blocks of the
+    forward transform are gathered and compared with the oracle; timings are device events, max over ranks."""
+    import numpy as np
+    fs = importlib.import_module(PKG + ".fourstep")
+    from oracle.pyoracle import Oracle
+    m = 22
+    N, q, psi = 1 << m, Q49, PSI[22]
+    a = splitmix64_mod(N, q, 4)
+    steps = 20
+    out = {"config": "one N=2^22 forward+inverse transform over %d GPUs" % world, "N": N,
+           "bytes_exchanged_per_gpu_per_direction": (N // world) * 8 * (world - 1) // world}
+
+    def reduce_ms(ms):
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # single-GPU time of the same transform (every rank measures its own GPU; max taken)
+    single = ntt.Plan.from_psi(N, q, psi, device=local)
+    ds = torch.from_numpy(a.view(np.int64)).cuda()
+    out["one_gpu_ms_per_pair"] = reduce_ms(timed_ms(torch, lambda: (single.fwd(ds, 1), single.inv(ds, 1)), steps))
+    single.close()
+    del ds
+
+    # NCCL all-to-all variant
+    plan = fs.DistributedNtt(N, q, psi, rank, world, device=local)
+    sl0 = torch.from_numpy(np.ascontiguousarray(a[rank::world]).view(np.int64)).cuda()
+    blk = plan.forward(sl0.clone(), dist)
+    gathered = [torch.empty_like(blk) for _ in range(world)] if rank == 0 else None
+    dist.gather(blk, gathered, dst=0)
+    ok_fwd = None
+    if rank == 0:
+        orc = Oracle()
+        t = oracle_tables(orc, m, q, psi)
+        want = orc.fwd(a, q, t["w"], t["wc"])
+        ok_fwd = bool(np.array_equal(torch.cat(gathered).cpu().numpy().view(np.uint64), want))
+    back = plan.inverse(blk, dist)
+    ok_rt = bool(torch.equal(back, sl0))
+
+    def step_nccl(state=[sl0.clone()]):
+        state[0] = plan.inverse(plan.forward(state[0], dist), dist)
+    dist.barrier()
+    out["nccl_ms_per_pair"] = reduce_ms(timed_ms(torch, step_nccl, steps))
+    plan.close()
+
+    # exchange fused into the tail kernels
+    fused = fs.FusedDistributedNtt(N, q, psi, rank, world, local, dist)
+    fused.px.load_slice(a[rank::world])
+    block = torch.empty(N // world, dtype=torch.int64, device="cuda")
+    fused.forward(block)
+    torch.cuda.synchronize()
+    gathered = [torch.empty_like(block) for _ in range(world)] if rank == 0 else None
+    dist.gather(block, gathered, dst=0)
+    ok_fused = None
+    if rank == 0:
+        ok_fused = bool(np.array_equal(torch.cat(gathered).cpu().numpy().view(np.uint64), want))
+    fused.inverse(block)
+    torch.cuda.synchronize()
+    ok_rt = ok_rt and bool(np.array_equal(fused.px.read_slice(), a[rank::world])) and not fused.px.timed_out()
+
+    def step_fused():
+        fused.forward(block)
+        fused.inverse(block)
+    dist.barrier()
+    out["peer_fused_ms_per_pair"] = reduce_ms(timed_ms(torch, step_fused, steps))
+    graph = fused.capture_pair(block)
+    dist.barrier()
+    out["peer_fused_graph_ms_per_pair"] = reduce_ms(timed_ms(torch, graph.replay, steps))
+    ok_rt = ok_rt and bool(np.array_equal(fused.px.read_slice(), a[rank::world])) and not fused.px.timed_out()
+    del graph
+    fused.close()
+    bad = torch.tensor([0.0 if ok_rt else 1.0], device="cuda")
+    dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+    best = min(out["peer_fused_ms_per_pair"], out["peer_fused_graph_ms_per_pair"])
+    out.update({
+        "forward_blocks_equal_oracle_nccl": ok_fwd, "forward_blocks_equal_oracle_peer_fused": ok_fused,
+        "round_trip_identity_all_ranks": bad.item() == 0.0,
+        "speedup_over_one_gpu": out["one_gpu_ms_per_pair"] / best,
+        # two exchanges per pair (forward gather, inverse scatter), each moving bytes_exchanged per GPU per direction
+        "nvlink_GBps_per_gpu_if_exchange_took_the_whole_pair": 2 * out["bytes_exchanged_per_gpu_per_direction"]
+                                                               / (best * 1e-3) / 1e9,
+    })
+    return out
 
 
 def run_b200_arm(args):
@@ -281,15 +509,21 @@ def run_b200_arm(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback")
     torch.cuda.set_device(local)
+    all_cpus = os.sched_getaffinity(0)
+    near = bind_near_gpu(local)                      # pinned buffers on the GPU's own NUMA node where NVML knows it
+    host_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        host_group = dist.new_group(backend="gloo")  # host-side barriers that put no kernel on the GPUs
+    D = dist if world > 1 else None
 
     N, batch = 1 << args.logn, args.batch
-    plan = ntt.Plan.from_psi(N, Q49, psi_for(args.logn, ntt), device=local)
+    psi = psi_for(args.logn, ntt)
+    plan = ntt.Plan.from_psi(N, Q49, psi, device=local)
+    fwd_kernels, fwd_launches = plan.describe(False)
+    inv_kernels, inv_launches = plan.describe(True)
 
-    # synthetic input: splitmix64 % q generated on the host by the product's own helper-free numpy code
-    rng = np.random.default_rng(1 + rank)
-    host = rng.integers(0, Q49, size=(batch, N), dtype=np.uint64)
+    host = splitmix64_mod(batch * N, Q49, 1 + rank).reshape(batch, N)
     pinned = torch.from_numpy(host.view(np.int64)).pin_memory()
     dev = pinned.cuda(non_blocking=False)
     stream = torch.cuda.current_stream()
@@ -298,12 +532,27 @@ def run_b200_arm(args):
         plan.fwd(dev, batch, stream)
         plan.inv(dev, batch, stream)
 
+    # ---- parity, outside the timed region: PARITY_ROWS random polynomials against the oracle, both directions ----
+    from oracle.pyoracle import Oracle
+    orc = Oracle()
+    tb = oracle_tables(orc, args.logn, Q49, psi)
+    rows = sorted(set(np.random.default_rng(99 + rank).integers(0, batch, size=PARITY_ROWS).tolist()) | {0, batch - 1})
+    plan.fwd(dev, batch, stream)
+    torch.cuda.synchronize()
+    fwd_rows = dev[rows].cpu().numpy().view(np.uint64)
+    fwd_ok = bool(np.array_equal(fwd_rows, orc.fwd_batch(host[rows], Q49, tb["w"], tb["wc"])))
+    plan.inv(dev, batch, stream)
+    torch.cuda.synchronize()
+    inv_ok = bool(np.array_equal(dev[rows].cpu().numpy().view(np.uint64),
+                                 orc.inv_batch(fwd_rows, Q49, tb["n_inv"], tb["wi"], tb["wic"])))
+    rt_ok = bool(torch.equal(dev, pinned.cuda()))
+    if not (fwd_ok and inv_ok and rt_ok):
+        raise SystemExit("bench.py: parity check failed (forward %s, inverse %s, round trip %s)" % (fwd_ok, inv_ok, rt_ok))
+    parity = {"rows_vs_oracle": len(rows), "forward": fwd_ok, "inverse": inv_ok, "round_trip_whole_batch": rt_ok}
+
     for _ in range(max(3, args.warmup)):
         step()
     torch.cuda.synchronize()
-    # correctness guard inside the bench: the round trip must reproduce the input exactly
-    if not torch.equal(dev, pinned.cuda()):
-        raise SystemExit("bench.py: forward+inverse round trip is not the identity")
 
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     sampler = ClockSampler(local)
@@ -311,8 +560,7 @@ def run_b200_arm(args):
         dist.barrier()
     torch.cuda.synchronize()
     sampler.start()
-    t_start = torch.cuda.Event(enable_timing=True)
-    t_end = torch.cuda.Event(enable_timing=True)
+    t_start, t_end = event_pair(torch)
     t_start.record(stream)
     for k in range(args.steps):
         ev[k][0].record(stream)
@@ -325,63 +573,163 @@ def run_b200_arm(args):
     if world > 1:
         dist.barrier()
     clocks = sampler.stop()
-    total_ms = sharding.reduce_max(t_start.elapsed_time(t_end), dist if world > 1 else None)
+    total_ms = sharding.reduce_max(t_start.elapsed_time(t_end), D)
     fwd_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
     inv_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
-
     ms_per_step = total_ms / args.steps
     value = 2.0 * batch * world / (ms_per_step * 1e-3)
+    if not torch.equal(dev, pinned.cuda()):
+        raise SystemExit("bench.py: the batch changed over the timed steps (round trip is not the identity)")
 
-    # end to end through the host-buffer C-ABI: pinned host memory, H2D + kernels + D2H inside the timing
+    # ---- sustained leg: the same step back to back for >= sustain-seconds, its own clock record ------------------
+    sustained = None
+    if not args.no_extras and args.sustain_seconds > 0:
+        n_sus = max(args.steps, int(args.sustain_seconds * 1e3 / ms_per_step) + 1)
+        s2 = ClockSampler(local)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        s2.start()
+        a0, a1 = event_pair(torch)
+        a0.record(stream)
+        for _ in range(n_sus):
+            step()
+        a1.record(stream)
+        torch.cuda.synchronize()
+        c2 = s2.stop()
+        sus_ms = sharding.reduce_max(a0.elapsed_time(a1), D) / n_sus
+        sustained = {"value": 2.0 * batch * world / (sus_ms * 1e-3), "unit": UNIT, "steps": n_sus,
+                     "seconds": sus_ms * n_sus * 1e-3, "ms_per_step": sus_ms, "clocks": c2}
+
+    # ---- end to end through the host-buffer C-ABI ------------------------------------------------------------
+    bytes_one_way = batch * N * 8
+    mult = splitmix64_mod(N, Q49, 777)                                  # NTT-domain multiplier, resident on the GPU
+    d_mult = torch.from_numpy(mult.view(np.int64)).cuda()
     e2e_steps = max(2, min(args.steps, 5))
-    plan.fwd_host(pinned, batch)
-    plan.inv_host(pinned, batch)  # warm-up (creates the staging pipeline)
+    track = host[rows].copy()                                           # the oracle follows these rows step by step
+
+    def oracle_fmi(x):
+        f = orc.fwd_batch(x, Q49, tb["w"], tb["wc"])
+        p = orc.pointwise_mul(f, np.ascontiguousarray(np.broadcast_to(mult, f.shape)), Q49).reshape(f.shape)
+        return orc.inv_batch(p, Q49, tb["n_inv"], tb["wi"], tb["wic"])
+
+    plan.fwd_mul_inv_host(pinned, d_mult, batch)                        # warm-up (creates the staging pipeline)
+    track = oracle_fmi(track)
     if world > 1:
-        dist.barrier()
+        dist.barrier(group=host_group)
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
+        plan.fwd_mul_inv_host(pinned, d_mult, batch)
+    e2e_s = sharding.reduce_max(time.perf_counter() - t0, D) / e2e_steps
+    for _ in range(e2e_steps):
+        track = oracle_fmi(track)
+    e2e_ok = bool(np.array_equal(pinned.numpy().view(np.uint64)[rows], track))
+    if not e2e_ok:
+        raise SystemExit("bench.py: host-path result differs from the oracle pipeline")
+    parity["e2e_rows_vs_oracle_after_%d_calls" % (e2e_steps + 1)] = e2e_ok
+    # the round-1 form: forward and inverse as two host calls (each crosses PCIe both ways)
+    pinned.copy_(torch.from_numpy(host.view(np.int64)))
+    plan.fwd_host(pinned, batch)
+    plan.inv_host(pinned, batch)
+    if world > 1:
+        dist.barrier(group=host_group)
+    t0 = time.perf_counter()
+    for _ in range(2):
         plan.fwd_host(pinned, batch)
         plan.inv_host(pinned, batch)
-    e2e_s = sharding.reduce_max(time.perf_counter() - t0, dist if world > 1 else None) / e2e_steps
+    sep_s = sharding.reduce_max(time.perf_counter() - t0, D) / 2
     if not np.array_equal(pinned.numpy().view(np.uint64), host):
         raise SystemExit("bench.py: host-path round trip is not the identity")
-    bytes_one_way = batch * N * 8
-    e2e = {"value": 2.0 * batch * world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 2 * bytes_one_way,
-           "d2h_bytes_per_step": 2 * bytes_one_way, "ms_per_step": e2e_s * 1e3,
-           "api": "ntt_b200_fwd_batch_host + ntt_b200_inv_batch_host, pinned host buffers"}
+    e2e = {"value": 2.0 * batch * world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": bytes_one_way,
+           "d2h_bytes_per_step": bytes_one_way, "ms_per_step": e2e_s * 1e3,
+           "api": "ntt_b200_fwd_mul_inv_batch_host (forward, NTT-domain product with a resident polynomial, inverse; "
+                  "one H2D and one D2H per polynomial), pinned host buffers%s" % (", CPU affinity set near the GPU" if near else ""),
+           "separate_calls": {"value": 2.0 * batch * world / sep_s, "ms_per_step": sep_s * 1e3,
+                              "h2d_bytes_per_step": 2 * bytes_one_way, "d2h_bytes_per_step": 2 * bytes_one_way,
+                              "api": "ntt_b200_fwd_batch_host + ntt_b200_inv_batch_host"}}
+    # what the box can copy: bare pinned H2D + D2H of the same bytes, both directions at once, all ranks together
+    if not args.no_extras:
+        other = torch.empty_like(pinned).pin_memory()
+        dev2 = torch.empty_like(dev)
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def copy_both():
+            with torch.cuda.stream(s_in):
+                dev.copy_(pinned, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                other.copy_(dev2, non_blocking=True)
+        copy_both()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=host_group)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            copy_both()
+        torch.cuda.synchronize()
+        cp_s = sharding.reduce_max(time.perf_counter() - t0, D) / 3
+        e2e["copy_bound"] = {"ms_per_step": cp_s * 1e3, "GBps_per_direction_per_gpu": bytes_one_way / cp_s / 1e9,
+                             "value_if_copies_were_all": 2.0 * batch * world / cp_s,
+                             "what": "pinned cudaMemcpyAsync H2D and D2H of one step's bytes, concurrently, all ranks at once"}
+        e2e["frac_of_copy_bound"] = cp_s / e2e_s
+        del other, dev2
 
     peak, peak_src = load_peak()
+    prof = load_profile_numbers()
     alg_bytes = 2.0 * N * 8 * batch  # per launch of the forward kernel: read + write every coefficient once
     achieved = alg_bytes / (fwd_ms * 1e-3) / 1e9
-    traffic = load_traffic(args.logn)
+    traffic = prof.get("fwd_logn%d_batch%d_dram_bytes_per_launch" % (args.logn, batch))
     roofline = {
-        "bound": "hbm", "kernel": "k_ring_fp<%d,fwd> (one launch = %d transforms)" % (args.logn, batch),
+        "bound": "hbm", "kernel": "%s (one launch = %d transforms)" % (fwd_kernels, batch),
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": None if traffic is None else traffic * batch, "peak_source": peak_src,
+        "traffic": traffic, "traffic_source": prof.get("traffic_source") if traffic else None,
+        "peak_source": peak_src,
         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": fwd_ms,
-        "compute_bound": load_compute_bound(batch / (fwd_ms * 1e-3)),
-        "inverse": {"kernel_ms": inv_ms, "achieved": alg_bytes / (inv_ms * 1e-3) / 1e9,
+        "issue_bound": issue_bound(prof, batch / (fwd_ms * 1e-3), clocks.get("sm_mhz")),
+        "inverse": {"kernel": inv_kernels, "kernel_ms": inv_ms, "achieved": alg_bytes / (inv_ms * 1e-3) / 1e9,
                     "frac": alg_bytes / (inv_ms * 1e-3) / 1e9 / peak},
         "fwd_ntt_per_s_per_gpu": batch / (fwd_ms * 1e-3), "inv_ntt_per_s_per_gpu": batch / (inv_ms * 1e-3),
     }
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        os.sched_setaffinity(0, all_cpus)            # the CPU baseline gets every host core again
         cpu = cpu_reference_rates(args.logn, args.cpu_seconds)
+
+    plan.close()
+    del dev, pinned
+    others = {}
+    if not args.no_extras:
+        torch.cuda.empty_cache()
+        try:
+            others["config3_rns"] = run_config3(ntt, torch, dist, rank, world, local, peak)
+        except Exception as e:  # the headline line must survive a failure in a side config
+            others["config3_rns"] = {"error": repr(e)}
+        if rank == 0:
+            try:
+                others["config4_polymul"] = run_config4(ntt, torch, peak)
+            except Exception as e:
+                others["config4_polymul"] = {"error": repr(e)}
+        if world > 1:
+            dist.barrier()
+            try:
+                others["config5_large_n"] = run_config5(ntt, torch, dist, rank, world, local)
+            except Exception as e:
+                others["config5_large_n"] = {"error": repr(e)}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, {"arithmetic": "u64 coefficients; butterflies are exact integer arithmetic "
-                                                           "carried in FP64 (q < 2^50), results bit-identical to the "
-                                                           "reference's 64-bit integer code"}),
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": 2 * args.steps * world, "clocks": clocks, "impl": "b200",
+            "config": workload_config(args),
+            "arm": "sm_100a kernels; u64 coefficients, butterflies are exact integer arithmetic carried in FP64 "
+                   "(q < 2^50), results bit-identical to the reference's 64-bit integer code",
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "sustained": sustained, "parity": parity,
+            "gpu_launches": (fwd_launches + inv_launches) * args.steps * world,
+            "kernels": {"forward": fwd_kernels, "inverse": inv_kernels},
+            "clocks": clocks, "impl": "b200", "other_configs": others,
         }
         print(json.dumps(line))
-    plan.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -389,6 +737,21 @@ def run_b200_arm(args):
 
 def main():
     args = parse_args()
+    # stdout carries exactly ONE JSON line: libraries that print there (NCCL's version banner, torchrun notices)
+    # are sent to stderr for the duration of the run and the line is written to the real stdout at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    import builtins
+    import io
+    out = io.TextIOWrapper(os.fdopen(real_stdout, "wb"), write_through=True)
+    py_print = builtins.print
+
+    def print_json(*a, **k):
+        k.setdefault("file", out)
+        py_print(*a, **k)
+    global print
+    print = print_json
     if args.impl == "reference":
         return run_reference_arm(args)
     return run_b200_arm(args)

@@ -87,6 +87,10 @@ int      ntt_b200_plan_device(const ntt_b200_plan_t *plan);
  * 0 if it uses the general Harvey path (any q < 2^62). */
 int ntt_b200_plan_is_lazy(const ntt_b200_plan_t *plan);
 
+/* Names of the kernels one forward (inverse != 0: inverse) transform of this plan launches, e.g.
+ * "k_strided<2> + k_ring_fp<14,fwd>", and their number -- so reports never hard-code them. */
+int ntt_b200_plan_describe(const ntt_b200_plan_t *plan, int inverse, char *buf, size_t n, int *launches);
+
 /*
  * Copy the plan's tables back to the host in REFERENCE format (each pointer may be NULL to skip):
  * what calc_w / calc_w_con / calc_w_inv would have produced (include/internal/pre_compute.h:38-77).

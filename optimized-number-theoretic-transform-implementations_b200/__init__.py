@@ -51,6 +51,7 @@ def _bind():
         getattr(L, f).argtypes = [vp]
     L.ntt_b200_plan_device.argtypes = [vp]
     L.ntt_b200_plan_is_lazy.argtypes = [vp]
+    L.ntt_b200_plan_describe.argtypes = [vp, i, C.c_char_p, sz, C.POINTER(i)]
     L.ntt_b200_plan_export_tables.argtypes = [vp, vp, vp, vp, vp, C.POINTER(u64), C.POINTER(u64)]
     for f in ("ntt_b200_fwd_batch", "ntt_b200_fwd_lazy_batch", "ntt_b200_inv_batch"):
         getattr(L, f).argtypes = [vp, vp, sz, vp]
@@ -120,7 +121,7 @@ EXPORTS = [
     "ntt_b200_last_error", "ntt_b200_device_count", "ntt_b200_version", "ntt_b200_configure",
     "ntt_b200_plan_create", "ntt_b200_plan_create_psi", "ntt_b200_plan_destroy",
     "ntt_b200_plan_n", "ntt_b200_plan_q", "ntt_b200_plan_device", "ntt_b200_plan_is_lazy",
-    "ntt_b200_plan_export_tables",
+    "ntt_b200_plan_export_tables", "ntt_b200_plan_describe",
     "ntt_b200_fwd_batch", "ntt_b200_fwd_lazy_batch", "ntt_b200_inv_batch",
     "ntt_b200_fwd_rns", "ntt_b200_inv_rns",
     "ntt_b200_fwd_tail_block", "ntt_b200_inv_tail_block", "ntt_b200_plan_set_inverse_scale",
@@ -300,6 +301,12 @@ class Plan:
     @property
     def device(self):
         return int(lib.ntt_b200_plan_device(self._h))
+
+    def describe(self, inverse=False):
+        """(kernel names, launches) of one transform, e.g. ("k_ring_fp<14,fwd>", 1)."""
+        buf, n = C.create_string_buffer(256), C.c_int()
+        _check(lib.ntt_b200_plan_describe(self._h, int(inverse), buf, 256, C.byref(n)), "plan_describe")
+        return buf.value.decode(), int(n.value)
 
     def export_tables(self, inverse=True):
         w = np.empty(self.N, dtype=np.uint64)

@@ -101,6 +101,8 @@ int ntt_cuda_gen_root_table(int device, uint64_t *d_w, uint64_t root, uint64_t N
 /* Transforms over `batch` contiguous polynomials of N = 2^logn words at d_a (in place). */
 int ntt_cuda_forward(int device, const ntt_cuda_params_t *p, uint64_t *d_a, size_t batch, void *stream);
 int ntt_cuda_inverse(int device, const ntt_cuda_params_t *p, uint64_t *d_a, size_t batch, void *stream);
+/* kernel names and launch count of one transform of this plan (for benchmark reports) */
+int ntt_cuda_describe(const ntt_cuda_params_t *p, int inverse, char *buf, size_t n, int *launches);
 /* RNS batch: limb l uses *plist[l] on d_a + l*batch_per_limb*N; limbs run concurrently on internal streams */
 int ntt_cuda_rns(int device, const ntt_cuda_params_t *const *plist, size_t limbs, uint64_t *d_a, size_t batch_per_limb,
                  int inverse, void *stream);

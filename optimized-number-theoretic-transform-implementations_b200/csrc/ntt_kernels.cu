@@ -929,6 +929,31 @@ static int inverse_impl(int device, const ntt_cuda_params_t &p, uint64_t *d_a, s
   return 0;
 }
 
+/* Which kernels a transform of this plan launches (what the dispatch above would do for 128-byte aligned data):
+ * buf receives e.g. "k_strided<2> + k_ring_fp<14,fwd>", *launches their number.  For benchmarks and reports. */
+extern "C" int ntt_cuda_describe(const ntt_cuda_params_t *p, int inverse, char *buf, size_t n, int *launches)
+{
+  if(!p || !buf || n == 0) return fail_msg("describe: NULL argument");
+  const Split sp  = make_split((int)p->logn);
+  const bool  fwd = !inverse;
+  char        chunk[64];
+  const bool  ring = ring_enabled() && p->lazy && sp.L >= 12 && sp.L <= 14 && (fwd ? p->fwd_ct_wu : p->inv_ct_wu);
+  if(ring && use_fp64(*p, fwd)) snprintf(chunk, sizeof(chunk), "k_ring_fp<%d,%s>", sp.L, fwd ? "fwd" : "inv");
+  else if(ring) snprintf(chunk, sizeof(chunk), "k_ring<%d,%s>", sp.L, fwd ? "fwd" : "inv");
+  else snprintf(chunk, sizeof(chunk), "k_chunk<%d,%s,%s>", sp.L, fwd ? "fwd" : "inv", p->lazy ? "lazy" : "exact");
+  size_t off = 0;
+  buf[0]     = 0;
+  if(fwd) {
+    for(int k = 0; k < sp.ns && off < n; k++) off += (size_t)snprintf(buf + off, n - off, "k_strided<%d> + ", sp.r[k]);
+    if(off < n) off += (size_t)snprintf(buf + off, n - off, "%s", chunk);
+  } else {
+    if(off < n) off += (size_t)snprintf(buf + off, n - off, "%s", chunk);
+    for(int k = sp.ns - 1; k >= 0 && off < n; k--) off += (size_t)snprintf(buf + off, n - off, " + k_strided<%d>", sp.r[k]);
+  }
+  if(launches) *launches = sp.ns + 1;
+  return 0;
+}
+
 extern "C" int ntt_cuda_forward(int device, const ntt_cuda_params_t *p, uint64_t *d_a, size_t batch, void *stream)
 {
   if(batch == 0) return 0;

@@ -342,6 +342,13 @@ uint64_t ntt_b200_plan_q(const ntt_b200_plan_t *plan) { return plan ? plan->q : 
 int      ntt_b200_plan_device(const ntt_b200_plan_t *plan) { return plan ? plan->device : -1; }
 int      ntt_b200_plan_is_lazy(const ntt_b200_plan_t *plan) { return plan ? (int)plan->params.lazy : 0; }
 
+int ntt_b200_plan_describe(const ntt_b200_plan_t *plan, int inverse, char *buf, size_t n, int *launches)
+{
+  if(!plan) return set_error("plan is NULL%s", NULL);
+  if(ntt_cuda_describe(&plan->params, inverse, buf, n, launches)) return cuda_error("describe");
+  return NTT_B200_SUCCESS;
+}
+
 int ntt_b200_plan_export_tables(const ntt_b200_plan_t *plan, uint64_t *w, uint64_t *w_con, uint64_t *w_inv,
                                 uint64_t *w_inv_con, uint64_t *n_inv, uint64_t *n_inv_con)
 {

@@ -1,0 +1,217 @@
+"""GPU tests of the round-2 entry points: the lazy forward, the fused forward-multiply-inverse (device and host
+buffers), squaring through negacyclic_mul, and the multi-GPU C API (device list in, batch sharded, no collective).
+All comparisons are bit-exact against the oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import CaseTables
+
+pytestmark = pytest.mark.gpu
+Q49 = 0x1FFFFFC800001
+
+
+def _torch():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+def _dev(a, device=0):
+    torch = _torch()
+    return torch.from_numpy(np.ascontiguousarray(a).view(np.int64)).to("cuda:%d" % device)
+
+
+def _host(t):
+    return t.cpu().numpy().view(np.uint64)
+
+
+def _setup(oracle, m, q=Q49):
+    N = 1 << m
+    psi = oracle.min_root(N, q)
+    return N, psi, CaseTables(oracle, m, q, psi, oracle.invmod(psi, q), oracle.invmod(N, q))
+
+
+def _q50(oracle, N):
+    q = (1 << 50) - ((1 << 50) - 1) % (2 * N)
+    while not oracle.is_prime(q) or q > (1 << 50) - 2048:
+        q -= 2 * N
+    return q
+
+
+@pytest.mark.parametrize("m,bits", [(14, 49), (14, 50), (13, 49), (12, 50), (16, 49), (10, 49), (14, 55)])
+def test_lazy_forward_contract(ntt, oracle, m, bits):
+    """ntt_b200_fwd_lazy_batch: output within the reference's lazy window [0,4q) and equal to fwd_ntt_ref_harvey
+    after reduce_4q_to_q (tests/test_correctness.c:267-269).  On the FP64 ring kernel the values really are
+    unreduced (some >= q), i.e. the entry point is not an alias of the reduced one."""
+    N = 1 << m
+    if bits == 49:
+        q = Q49
+    elif bits == 50:
+        q = _q50(oracle, N)
+    else:
+        q = (1 << 55) - ((1 << 55) - 1) % (2 * N)
+        while not oracle.is_prime(q):
+            q -= 2 * N
+    N, psi, t = _setup(oracle, m, q)
+    batch = 64
+    a = oracle.uniform(batch * N, 4 * q, 21).reshape(batch, N)
+    plan = ntt.Plan.from_psi(N, q, psi)
+    d = _dev(a)
+    plan.fwd_lazy(d, batch)
+    lazy = _host(d)
+    want = oracle.fwd_batch(a, q, t.w, t.w_con)
+    assert (lazy < 4 * q).all()
+    assert np.array_equal(lazy % np.uint64(q), want)
+    if bits <= 50 and m >= 12:
+        assert (lazy < 2 * q).all() and (lazy >= q).any(), "the FP64 ring kernel should skip the sign correction"
+    plan.close()
+
+
+@pytest.mark.parametrize("m,bits", [(14, 49), (13, 49), (14, 50), (16, 49), (11, 49), (14, 55)])
+def test_fwd_mul_inv_device(ntt, oracle, m, bits):
+    """a <- INTT(NTT(a) .* m) with ONE multiplier broadcast over the batch, against the oracle pipeline."""
+    N = 1 << m
+    if bits == 49:
+        q = Q49
+    elif bits == 50:
+        q = _q50(oracle, N)
+    else:
+        q = (1 << 55) - ((1 << 55) - 1) % (2 * N)
+        while not oracle.is_prime(q):
+            q -= 2 * N
+    N, psi, t = _setup(oracle, m, q)
+    batch = 37
+    a = oracle.uniform(batch * N, q, 5).reshape(batch, N)
+    mult = oracle.uniform(N, q, 6)                              # NTT-domain multiplier, canonical residues
+    fa = oracle.fwd_batch(a, q, t.w, t.w_con)
+    prod = oracle.pointwise_mul(fa, np.ascontiguousarray(np.broadcast_to(mult, (batch, N))), q).reshape(batch, N)
+    want = oracle.inv_batch(prod, q, t.n_inv, t.w_inv, t.w_inv_con)
+    plan = ntt.Plan.from_psi(N, q, psi)
+    d, dm = _dev(a), _dev(mult)
+    plan.fwd_mul_inv(d, dm, batch)
+    assert np.array_equal(_host(d), want)
+    # NULL multiplier: plain round trip
+    d = _dev(a)
+    plan.fwd_mul_inv(d, None, batch)
+    assert np.array_equal(_host(d), a)
+    # host-buffer form (pinned and pageable), chunked pipeline: make the batch span several chunks
+    torch = _torch()
+    big = max(batch, (96 << 20) // (N * 8) + 3)
+    ab = oracle.uniform(big * N, q, 8).reshape(big, N)
+    fb = oracle.fwd_batch(ab, q, t.w, t.w_con)
+    pb = oracle.pointwise_mul(fb, np.ascontiguousarray(np.broadcast_to(mult, (big, N))), q).reshape(big, N)
+    wb = oracle.inv_batch(pb, q, t.n_inv, t.w_inv, t.w_inv_con)
+    pinned = torch.from_numpy(ab.copy().view(np.int64)).pin_memory()
+    plan.fwd_mul_inv_host(pinned, dm, big)
+    assert np.array_equal(pinned.numpy().view(np.uint64), wb)
+    pageable = ab.copy()
+    plan.fwd_mul_inv_host(pageable, dm, big)
+    assert np.array_equal(pageable, wb)
+    # the separate host calls still agree with the oracle on the same multi-chunk batch
+    h = ab.copy()
+    plan.fwd_host(h, big)
+    assert np.array_equal(h, fb)
+    plan.inv_host(h, big)
+    assert np.array_equal(h, ab)
+    plan.close()
+
+
+@pytest.mark.parametrize("m,bits", [(13, 49), (14, 49), (10, 49), (13, 55)])
+def test_negacyclic_square(ntt, oracle, m, bits):
+    """d_a == d_b (squaring) used to return garbage: now one forward, a pointwise square, the inverse."""
+    N = 1 << m
+    q = Q49
+    if bits == 55:
+        q = (1 << 55) - ((1 << 55) - 1) % (2 * N)
+        while not oracle.is_prime(q):
+            q -= 2 * N
+    N, psi, t = _setup(oracle, m, q)
+    batch = 5
+    a = oracle.uniform(batch * N, q, 9).reshape(batch, N)
+    fa = oracle.fwd_batch(a, q, t.w, t.w_con)
+    want = oracle.inv_batch(oracle.pointwise_mul(fa, fa, q).reshape(batch, N), q, t.n_inv, t.w_inv, t.w_inv_con)
+    plan = ntt.Plan.from_psi(N, q, psi)
+    d = _dev(a)
+    plan.negacyclic_mul(d, d, d, batch)                         # c = a = b
+    assert np.array_equal(_host(d), want)
+    d, c = _dev(a), _dev(np.zeros_like(a))
+    plan.negacyclic_mul(c, d, d, batch)                         # separate output
+    assert np.array_equal(_host(c), want)
+    if m <= 10:                                                 # schoolbook cross-check of the first polynomial
+        assert np.array_equal(want[0], oracle.negacyclic_mul(a[0], a[0], q))
+    plan.close()
+
+
+def test_multi_gpu_c_api(ntt, oracle):
+    """ntt_b200_multi_*: every visible GPU gets a contiguous shard; device-resident and host-buffer forms;
+    results equal the oracle row for row whatever the device count (1 on the test box, 2..8 on a bigger one)."""
+    torch = _torch()
+    ndev = torch.cuda.device_count()
+    m = 13
+    N, psi, t = _setup(oracle, m)
+    q = Q49
+    batch = 8 * ndev + 5                                        # ragged: shards differ by one
+    a = oracle.uniform(batch * N, q, 31).reshape(batch, N)
+    want = oracle.fwd_batch(a, q, t.w, t.w_con)
+    mp = ntt.MultiPlan(N, q, psi, list(range(ndev)))
+    shards = [mp.shard(batch, i) for i in range(ndev)]
+    assert sum(c for _, c in shards) == batch and shards[0][0] == 0
+    assert all(shards[i][0] + shards[i][1] == shards[i + 1][0] for i in range(ndev - 1))
+    bufs = [_dev(a[f:f + c], i) for i, (f, c) in enumerate(shards)]
+    mp.fwd(bufs, [c for _, c in shards])
+    mp.sync()
+    got = np.concatenate([_host(b) for b in bufs])
+    assert np.array_equal(got, want)
+    mp.inv(bufs, [c for _, c in shards])
+    mp.sync()
+    assert np.array_equal(np.concatenate([_host(b) for b in bufs]), a)
+    # host-buffer forms: one host thread per device
+    h = a.copy()
+    mp.fwd_host(h, batch)
+    assert np.array_equal(h, want)
+    mp.inv_host(h, batch)
+    assert np.array_equal(h, a)
+    mult = oracle.uniform(N, q, 32)
+    dms = [_dev(mult, i) for i in range(ndev)]
+    prod = oracle.pointwise_mul(want, np.ascontiguousarray(np.broadcast_to(mult, (batch, N))), q).reshape(batch, N)
+    want2 = oracle.inv_batch(prod, q, t.n_inv, t.w_inv, t.w_inv_con)
+    mp.fwd_mul_inv_host(h, dms, batch)
+    assert np.array_equal(h, want2)
+    mp.close()
+
+
+def test_rns_limbs_sharded_over_devices(ntt, oracle):
+    """ntt_b200_fwd_rns_multi / inv: limb l on device l mod ndev, each with its own modulus (config 3 shape)."""
+    torch = _torch()
+    ndev = torch.cuda.device_count()
+    m, limbs, per = 13, 6, 3
+    N = 1 << m
+    qs, q = [], (1 << 50) + 1
+    while len(qs) < limbs:
+        q -= 2 * N
+        if oracle.is_prime(q) and q <= (1 << 50) - 2048:
+            qs.append(q)
+    plans, bufs, wants, ins = [], [], [], []
+    for l, ql in enumerate(qs):
+        dev = l * ndev // limbs                                  # contiguous runs of limbs per device
+        psi = oracle.min_root(N, ql)
+        t = CaseTables(oracle, m, ql, psi, oracle.invmod(psi, ql), oracle.invmod(N, ql))
+        a = oracle.uniform(per * N, ql, 40 + l).reshape(per, N)
+        plans.append(ntt.Plan.from_psi(N, ql, psi, device=dev))
+        bufs.append(_dev(a, dev))
+        ins.append(a)
+        wants.append(oracle.fwd_batch(a, ql, t.w, t.w_con))
+    ntt.rns_multi(plans, bufs, per)
+    for i in range(ndev):
+        ntt.device_sync(i)
+    for l in range(limbs):
+        assert np.array_equal(_host(bufs[l]), wants[l]), "limb %d" % l
+    ntt.rns_multi(plans, bufs, per, inverse=True)
+    for i in range(ndev):
+        ntt.device_sync(i)
+    for l in range(limbs):
+        assert np.array_equal(_host(bufs[l]), ins[l]), "limb %d round trip" % l
+    for p in plans:
+        p.close()

@@ -94,18 +94,30 @@ def test_distributed_transform_nccl(ntt, oracle, m):
 
 # ---- exchange fused into the tail kernels (peer loads / stores instead of a collective) -------------------
 
-@pytest.mark.parametrize("m,world", [(16, 2), (18, 4), (20, 8), (14, 32)])
-def test_peer_gather_scatter_emulated_on_one_gpu(ntt, oracle, m, world):
+def _prime_below(oracle, bits, N):
+    q = (1 << bits) - ((1 << bits) - 1) % (2 * N)
+    while not oracle.is_prime(q):
+        q -= 2 * N
+    return q
+
+
+@pytest.mark.parametrize("m,world,qbits", [(16, 2, 49), (18, 4, 49), (20, 8, 49), (14, 32, 49), (14, 32, 55),
+                                           (22, 32, 55), (16, 16, 56)])
+def test_peer_gather_scatter_emulated_on_one_gpu(ntt, oracle, m, world, qbits):
     """ntt_b200_fwd_tail_gather / ntt_b200_inv_tail_scatter with every rank's slice on the same GPU (the "peer"
-    pointers are local): same result as the reference transform, no all-to-all and no interleave copy."""
+    pointers are local): same result as the reference transform, no all-to-all and no interleave copy.
+    qbits = 55 / 56: the inverse tail's own lazy bounds (the size-N plan schedules a renormalisation inside the
+    tail's five stages for q above about 2^51.7, which a single register network would skip)."""
     import ctypes as C
     import torch
     fourstep = importlib.import_module(PKG + ".fourstep")
-    N, q, G = 1 << m, Q49, world
+    N, G = 1 << m, world
+    q = Q49 if qbits == 49 else _prime_below(oracle, qbits, N)
     g = G.bit_length() - 1
     psi = _root(oracle, N, q)
     t = CaseTables(oracle, m, q, psi, oracle.invmod(psi, q), oracle.invmod(N, q))
     a = oracle.uniform(N, 4 * q, 6)                       # forward contract [0,4q)
+    a[: N // 64] = 4 * q - 1
     parts = [fourstep.DistributedNtt(N, q, psi, r, G) for r in range(G)]
     slices = [torch.from_numpy(np.ascontiguousarray(a[p::G]).view(np.int64)).cuda() for p in range(G)]
     ptrs = (C.c_void_p * G)(*[s.data_ptr() for s in slices])
