@@ -32,6 +32,7 @@
  * slots hold doubles instead of u64.
  */
 #pragma once
+#include "ntt_fp_schedule.h"
 #include "ntt_ring.cuh"
 
 namespace nttb200 {
@@ -39,36 +40,26 @@ namespace nttb200 {
 struct FpC {
   double q, qinv, magic;
 };
-#define NTT_FP_MAGIC 6755399441055744.0 /* 1.5 * 2^52 */
+#define NTT_FP_MAGIC 6755399441055744.0   /* 1.5 * 2^52: rounds |arg| < 2^51 to the nearest integer */
+#define NTT_FP_MAGIC2 13510798882111488.0 /* 3 * 2^52:   rounds |arg| < 2^52 to the nearest EVEN integer */
 
-/* v - rint(v/q)*q: |result| <= 0.51 q for |v| < 2^53 (q < 2^49) */
+/* v - rint(v/q)*q: |result| <= q/2 + 6 for |v| < 2^53 */
 __device__ __forceinline__ double fp_fold(double v, const FpC &c)
 {
   const double k = __dadd_rn(__fma_rn(v, c.qinv, c.magic), -c.magic);
   return __fma_rn(-k, c.q, v);
 }
-/* t == w*y (mod q), exact integer, small (see the header) */
+/* t == w*y (mod q), exact integer.  COARSE = false: |y*winv| < 2^51, |t| <= q*(1/2 + |y|*2^-54);
+ * COARSE = true: |y*winv| < 2^52, the quotient is rounded to an even integer, |t| <= q*(1 + |y|*2^-54).
+ * Six FP64 instructions either way (tools/gen_fp_schedule.py decides which one a butterfly gets). */
+template <bool COARSE = false>
 __device__ __forceinline__ double fp_mul(double y, double w, double winv, const FpC &c)
 {
-  const double cc = __dadd_rn(__fma_rn(y, winv, c.magic), -c.magic);
-  const double h  = __dmul_rn(y, w);
-  const double l  = __fma_rn(y, w, -h);
-  const double d  = __fma_rn(-cc, c.q, h);
-  return __dadd_rn(d, l);
-}
-/* Same product for |y| < 2^52 (inverse passes, where X - Y reaches 8q): the magic-constant rounding above is
- * only an integer for |y*winv| < 2^51 (a negative argument beyond that lands where ulp = 1/2), so round the
- * magnitude with 2^52 instead -- exact for |arg| < 2^52 -- and put the sign on q: d = h - sign(arg)*c*q.
- * 7 FP64 instructions + 1 LOP3. */
-__device__ __forceinline__ double fp_mul_wide(double y, double w, double winv, const FpC &c)
-{
-  const double arg = __dmul_rn(y, winv);
-  const double ca  = __dadd_rn(__dadd_rn(fabs(arg), 4503599627370496.0), -4503599627370496.0);
-  const double qs  = __hiloint2double(__double2hiint(c.q) ^ (int)((~(uint32_t)__double2hiint(arg)) & 0x80000000u),
-                                      __double2loint(c.q)); /* -q if arg >= 0, +q if arg < 0 */
-  const double h   = __dmul_rn(y, w);
-  const double l   = __fma_rn(y, w, -h);
-  const double d   = __fma_rn(ca, qs, h);
+  constexpr double M  = COARSE ? NTT_FP_MAGIC2 : NTT_FP_MAGIC;
+  const double     cc = __dadd_rn(__fma_rn(y, winv, M), -M);
+  const double     h  = __dmul_rn(y, w);
+  const double     l  = __fma_rn(y, w, -h);
+  const double     d  = __fma_rn(-cc, c.q, h);
   return __dadd_rn(d, l);
 }
 /* u64 below 2^52 -> the same integer as a double (exponent splice + one DADD) */
@@ -78,18 +69,28 @@ __device__ __forceinline__ double fp_from_u64(uint64_t v, double neg_bias = -450
   return __dadd_rn(__hiloint2double((int)(hi32(v) | 0x43300000u), (int)lo32(v)), neg_bias);
 }
 /* |v| < q, integer  ->  canonical residue in [0,q) as u64.  One DADD puts v next to 1.5*2^52, where consecutive
- * integers are consecutive bit patterns; the rest (subtract the constant's bits, add q to negatives) is integer
- * work on the otherwise idle ALU pipe. */
+ * integers are consecutive bit patterns; the rest is integer work: subtract the constant's bits and add q to
+ * negatives (v < 0 <=> the high word is below the constant's, whose low word is 0).  Written in PTX so that it
+ * stays at compare + two selects + add-with-carry. */
 __device__ __forceinline__ uint64_t fp_to_u64(double v, const FpC &c, uint64_t q)
 {
-  const double   t  = __dadd_rn(v, c.magic);
-  const uint32_t hi = (uint32_t)__double2hiint(t), lo = (uint32_t)__double2loint(t);
-  /* bits(t) - bits(magic) = v as a signed integer; v < 0 <=> t < magic <=> hi < 0x43380000 (magic's low word is 0),
-   * so the sign test is one 32-bit compare */
-  const uint64_t r = ((uint64_t)(hi - 0x43380000u) << 32) | lo;
-  return r + (hi < 0x43380000u ? q : 0ull);
+  const double   t   = __dadd_rn(v, c.magic);
+  const uint32_t hi  = (uint32_t)__double2hiint(t), lo = (uint32_t)__double2loint(t);
+  const uint32_t qlo = lo32(q), qhi = hi32(q);
+  uint32_t       rlo, rhi;
+  asm("{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .u32 alo, ahi;\n\t"
+      "setp.lt.u32 p, %2, 0x43380000;\n\t"
+      "selp.u32 alo, %4, 0, p;\n\t"
+      "selp.u32 ahi, %5, 0xbcc80000, p;\n\t" /* -0x43380000 (+ q's high word for negatives) */
+      "add.cc.u32 %0, %3, alo;\n\t"
+      "addc.u32 %1, %2, ahi;\n\t"
+      "}"
+      : "=r"(rlo), "=r"(rhi)
+      : "r"(hi), "r"(lo), "r"(qlo), "r"(qhi + 0xbcc80000u));
+  return ((uint64_t)rhi << 32) | rlo;
 }
-
 /* |v| < q, integer -> v + q in (0, 2q) as u64: the lazy representative, no sign test (bias = 1.5*2^52 + q) */
 __device__ __forceinline__ uint64_t fp_to_u64_lazy(double v, double bias)
 {
@@ -98,123 +99,138 @@ __device__ __forceinline__ uint64_t fp_to_u64_lazy(double v, double bias)
   return ((uint64_t)(hi - 0x43380000u) << 32) | lo;
 }
 
-__device__ __forceinline__ void fp_bfly_fwd(double &x, double &y, double2 tw, const FpC &c)
-{
-  const double t = fp_mul(y, tw.x, tw.y, c);
-  y              = __dadd_rn(x, -t);
-  x              = __dadd_rn(x, t);
-}
-/* WIDE: the difference may exceed 2^51 (fourth stage after a fold), use the rounding that is exact up to 2^52 */
-template <bool WIDE>
-__device__ __forceinline__ void fp_bfly_inv(double &x, double &y, double2 tw, const FpC &c)
-{
-  const double d = __dadd_rn(x, -y);
-  x              = __dadd_rn(x, y);
-  y              = WIDE ? fp_mul_wide(d, tw.x, tw.y, c) : fp_mul(d, tw.x, tw.y, c);
-}
-
-/* forward butterfly whose multiplied operand may reach 4q (50-bit schedule, fourth stage of pass C) */
-__device__ __forceinline__ void fp_bfly_fwd_wide(double &x, double &y, double2 tw, const FpC &c)
-{
-  const double t = fp_mul_wide(y, tw.x, tw.y, c);
-  y              = __dadd_rn(x, -t);
-  x              = __dadd_rn(x, t);
-}
-
 /*
- * R-stage network; TWF(t) returns twiddle entry t = 2^u-1+sub of this group.  Inputs are folded first.
- * FINAL: the inverse network ends with global stage 0, whose two products carry N^-1
- * (harvey_bkw_butterfly_final, fast_mul_operators.h:94-106).
- *
- * ROLE (forward, first schedule only): 0 = middle pass, 1 = first pass (input centred to [-2q,2q) by the
- * conversion, no fold), 2 = last pass (no fold, the caller folds the results).
- *
- * Range schedules (values in units of q; product bounds from the header: plain 1/2 + y/32, wide 3/4 + y/32
- * for q/2^52 < 1/8, and twice the y-terms for q/2^52 < 1/4):
- *   Q50 = false, q <= 2^49 - 1024:
- *     forward  a plain product needs its operand below 4q = 2^51, a wide one below 8q:
- *              pass A from 2:    2 -> 2.57 -> 3.15 -> 3.75 -> 4.36 (fifth stage wide) -> 5.25
- *              pass B from fold: 0.5 -> 1.02 -> 1.55 -> 2.10 -> 2.67 -> 3.25
- *              pass C unfolded:  3.25 -> 3.85 -> 4.47 (wide from here) -> 5.36 -> 6.28, then the final fold;
- *     inverse  sums 0.5 -> 1 -> 2 -> 4 -> 8: differences reach 8q < 2^52 at n = 4 (wide rounding), a 5-stage
- *              pass folds again after three stages.
- *   Q50 = true, q <= 2^50 - 2048 (every pass folds first):
- *     forward  0.5 -> 1.13 -> 1.91 -> 2.88 -> 4.10: the operand is below 2q < 2^51 for n <= 3, below 4q < 2^52
- *              at n = 4 (wide rounding), so a 5-stage pass folds again after three stages;
- *     inverse  differences are 1, 2, 4 q at n = 1, 2, 3 (wide rounding from n = 2) and every pass folds
- *              again after three stages.
- * tests/test_fp64_arith_model.py mirrors these schedules and checks every operand against its limit.
+ * Register networks.  Which positions are folded before a stage, which butterflies round coarsely and which
+ * positions are folded after the last stage come from the generated tables of ntt_fp_schedule.h
+ * (tools/gen_fp_schedule.py: exact-rational bound propagation, re-checked by tests/test_fp64_arith_model.py).
+ *   forward (X' = X + t, Y' = X - t): all positions share one bound, so a fold is all-or-nothing per stage;
+ *   inverse (X' = X + Y, Y' = t(X - Y)): sums double but products come back small, so only the few positions
+ *   whose bound would break a limit are folded.
+ * KIND 0 forward, 1 inverse (pass A ends with the N^-1 stage), 2 inverse of a chunk of a larger transform.
+ * WHICH 0 / 1 / 2 = pass A / B / C.
  */
+template <int KIND, bool Q50, int L, int WHICH>
+struct FpSel {
+  static __host__ __device__ constexpr FpPass get()
+  {
+    const FpSchedule &s = KIND == 0 ? FP_SCHED_FWD[Q50][L - 12]
+                                    : (KIND == 1 ? FP_SCHED_INV[Q50][L - 12] : FP_SCHED_INV_NOFINAL[Q50][L - 12]);
+    return WHICH == 0 ? s.a : (WHICH == 1 ? s.b : s.c);
+  }
+};
 struct FpNoHook {
   __device__ __forceinline__ void operator()() const {}
 };
-/* MIDF: called once after the second stage of a forward network (the forward kernel re-arms a ring slot there) */
-template <int R, bool FWD, bool FINAL, bool Q50, int ROLE, typename TWF, typename MIDF = FpNoHook>
-__device__ __forceinline__ void fp_network(double (&x)[1 << R], const FpC &c, const ntt_cuda_params_t &p, TWF twf,
-                                           MIDF mid = MIDF())
+
+template <int R, uint32_t MASK>
+__device__ __forceinline__ void fp_fold_mask(double (&x)[1 << R], const FpC &c)
 {
-  constexpr int  n    = 1 << R;
-  constexpr bool lean = FWD && !Q50 && ROLE != 0; /* first / last forward pass of the first schedule: no fold */
-  if(!lean) {
 #pragma unroll
-    for(int k = 0; k < n; k++) x[k] = fp_fold(x[k], c);
+  for(int k = 0; k < (1 << R); k++) {
+    if((MASK >> k) & 1u) x[k] = fp_fold(x[k], c);
   }
-  if(FWD) {
+}
+
+/* forward stage u of an R-stage network: pairs at distance n >> (u+1), sub-block `sub` uses twiddle 2^u-1+sub */
+template <int R, int U, uint32_t COARSE, typename TWF>
+__device__ __forceinline__ void fp_fwd_stage(double (&x)[1 << R], const FpC &c, TWF &twf)
+{
+  constexpr int n = 1 << R, d = n >> (U + 1);
 #pragma unroll
-    for(int u = 0; u < R; u++) {
-      const int d = n >> (u + 1);
-      if(Q50 && R == 5 && u == 3) {
+  for(int sub = 0; sub < (1 << U); sub++) {
+    const double2 tw = twf((1 << U) - 1 + sub);
 #pragma unroll
-        for(int k = 0; k < n; k++) x[k] = fp_fold(x[k], c);
-      }
+    for(int k = 0; k < d; k++) {
+      const int    lo = sub * 2 * d + k;
+      const double t  = ((COARSE >> lo) & 1u) ? fp_mul<true>(x[lo + d], tw.x, tw.y, c) : fp_mul<false>(x[lo + d], tw.x, tw.y, c);
+      x[lo + d]       = __dadd_rn(x[lo], -t);
+      x[lo]           = __dadd_rn(x[lo], t);
+    }
+  }
+}
+
+/* MIDF: called once after the second stage (the forward kernel re-arms a ring slot there) */
+template <int R, typename SEL, typename TWF, typename MIDF = FpNoHook>
+__device__ __forceinline__ void fp_network_fwd(double (&x)[1 << R], const FpC &c, TWF twf, MIDF mid = MIDF())
+{
+  constexpr FpPass S = SEL::get();
+  fp_fold_mask<R, S.fold_before[0]>(x, c);
+  fp_fwd_stage<R, 0, S.coarse[0]>(x, c, twf);
+  if constexpr(R > 1) {
+    fp_fold_mask<R, S.fold_before[1]>(x, c);
+    fp_fwd_stage<R, 1, S.coarse[1]>(x, c, twf);
+  }
+  mid();
+  if constexpr(R > 2) {
+    fp_fold_mask<R, S.fold_before[2]>(x, c);
+    fp_fwd_stage<R, 2, S.coarse[2]>(x, c, twf);
+  }
+  if constexpr(R > 3) {
+    fp_fold_mask<R, S.fold_before[3]>(x, c);
+    fp_fwd_stage<R, 3, S.coarse[3]>(x, c, twf);
+  }
+  if constexpr(R > 4) {
+    fp_fold_mask<R, S.fold_before[4]>(x, c);
+    fp_fwd_stage<R, 4, S.coarse[4]>(x, c, twf);
+  }
+  fp_fold_mask<R, S.fold_end>(x, c);
+}
+
+/* inverse stage number ST in processing order (network stage u = R-1-ST): pairs at distance 2^ST.
+ * LAST: global stage 0, both outputs are products carrying N^-1 (harvey_bkw_butterfly_final,
+ * fast_mul_operators.h:94-106); the schedule guarantees plain rounding there, so |t| < q and the results are
+ * converted without another fold. */
+template <int R, int ST, uint32_t COARSE, bool LAST, typename TWF>
+__device__ __forceinline__ void fp_inv_stage(double (&x)[1 << R], const FpC &c, const ntt_cuda_params_t &p, TWF &twf)
+{
+  constexpr int U = R - 1 - ST, d = 1 << ST;
+  if constexpr(LAST) {
+    static_assert(U == 0 && COARSE == 0, "the N^-1 stage is the last one and rounds plainly");
+    const double2 a = make_double2(p.ninv_fd[0], p.ninv_fd[1]), b = make_double2(p.ninv_w1_fd[0], p.ninv_w1_fd[1]);
 #pragma unroll
-      for(int sub = 0; sub < (1 << u); sub++) {
-        const double2 tw = twf((1 << u) - 1 + sub);
-#pragma unroll
-        for(int k = 0; k < d; k++) {
-          const bool wide = Q50 ? (R == 4 && u == 3) : (ROLE == 1 ? u >= 4 : (ROLE == 2 ? u >= 2 : false));
-          if(wide) fp_bfly_fwd_wide(x[sub * 2 * d + k], x[sub * 2 * d + k + d], tw, c);
-          else fp_bfly_fwd(x[sub * 2 * d + k], x[sub * 2 * d + k + d], tw, c);
-        }
-      }
-      if(u == 1) mid();
+    for(int k = 0; k < d; k++) {
+      const double s = __dadd_rn(x[k], x[k + d]), df = __dadd_rn(x[k], -x[k + d]);
+      x[k]           = fp_mul<false>(s, a.x, a.y, c);
+      x[k + d]       = fp_mul<false>(df, b.x, b.y, c);
     }
   } else {
 #pragma unroll
-    for(int u = R - 1; u >= 0; u--) {
-      const int d = n >> (u + 1);
-      /* second fold after three stages: every 5-stage pass, and 4-stage passes on the 50-bit schedule */
-      const bool refold = (R == 5 && u == 1) || (Q50 && R == 4 && u == 0);
-      if(refold) {
+    for(int sub = 0; sub < (1 << U); sub++) {
+      const double2 tw = twf((1 << U) - 1 + sub);
 #pragma unroll
-        for(int k = 0; k < n; k++) x[k] = fp_fold(x[k], c);
-      }
-      /* stages since the last fold, counting this one */
-      const int since = (R == 5) ? (u >= 2 ? 5 - u : 2 - u) : ((Q50 && R == 4 && u == 0) ? 1 : R - u);
-      const bool wide = Q50 ? since >= 2 : since >= 4;
-      if(FINAL && u == 0) {
-        /* sums reach 8q (49-bit, R = 4) or 4q (50-bit, R = 3): still below 2^52, so the products are below q in
-         * magnitude (bound in the header) and are converted without another fold */
-        const double2 a = make_double2(p.ninv_fd[0], p.ninv_fd[1]), b = make_double2(p.ninv_w1_fd[0], p.ninv_w1_fd[1]);
-#pragma unroll
-        for(int k = 0; k < d; k++) {
-          const double s = __dadd_rn(x[k], x[k + d]), df = __dadd_rn(x[k], -x[k + d]);
-          x[k]           = fp_mul_wide(s, a.x, a.y, c);
-          x[k + d]       = fp_mul_wide(df, b.x, b.y, c);
-        }
-      } else {
-#pragma unroll
-        for(int sub = 0; sub < (1 << u); sub++) {
-          const double2 tw = twf((1 << u) - 1 + sub);
-#pragma unroll
-          for(int k = 0; k < d; k++) {
-            if(wide) fp_bfly_inv<true>(x[sub * 2 * d + k], x[sub * 2 * d + k + d], tw, c);
-            else fp_bfly_inv<false>(x[sub * 2 * d + k], x[sub * 2 * d + k + d], tw, c);
-          }
-        }
+      for(int k = 0; k < d; k++) {
+        const int    lo = sub * 2 * d + k;
+        const double df = __dadd_rn(x[lo], -x[lo + d]);
+        x[lo]           = __dadd_rn(x[lo], x[lo + d]);
+        x[lo + d]       = ((COARSE >> lo) & 1u) ? fp_mul<true>(df, tw.x, tw.y, c) : fp_mul<false>(df, tw.x, tw.y, c);
       }
     }
   }
+}
+
+template <int R, bool FINAL, typename SEL, typename TWF>
+__device__ __forceinline__ void fp_network_inv(double (&x)[1 << R], const FpC &c, const ntt_cuda_params_t &p, TWF twf)
+{
+  constexpr FpPass S = SEL::get();
+  fp_fold_mask<R, S.fold_before[0]>(x, c);
+  fp_inv_stage<R, 0, S.coarse[0], FINAL && R == 1>(x, c, p, twf);
+  if constexpr(R > 1) {
+    fp_fold_mask<R, S.fold_before[1]>(x, c);
+    fp_inv_stage<R, 1, S.coarse[1], FINAL && R == 2>(x, c, p, twf);
+  }
+  if constexpr(R > 2) {
+    fp_fold_mask<R, S.fold_before[2]>(x, c);
+    fp_inv_stage<R, 2, S.coarse[2], FINAL && R == 3>(x, c, p, twf);
+  }
+  if constexpr(R > 3) {
+    fp_fold_mask<R, S.fold_before[3]>(x, c);
+    fp_inv_stage<R, 3, S.coarse[3], FINAL && R == 4>(x, c, p, twf);
+  }
+  if constexpr(R > 4) {
+    fp_fold_mask<R, S.fold_before[4]>(x, c);
+    fp_inv_stage<R, 4, S.coarse[4], FINAL && R == 5>(x, c, p, twf);
+  }
+  fp_fold_mask<R, S.fold_end>(x, c);
 }
 
 /* -DNTT_RING_TRACE: CTA 0 records clock64() at the phase boundaries of its first 64 polynomials (read back with
@@ -262,8 +278,8 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
   const size_t   my_blocks = my_polys * NB;
   const size_t   groups    = (size_t)1 << (p.logn - 4);
   const FpC      c{p.q_fd, p.qinv_fd, NTT_FP_MAGIC};
-  /* forward input [0,4q) is centred to [-2q,2q) by the conversion itself on the first schedule (see fp_network) */
-  const double   in_bias = -(4503599627370496.0 + ((FWD && !Q50) ? 2.0 * p.q_fd : 0.0));
+  /* the conversion centres the input: forward [0,4q) -> [-2q,2q), inverse [0,2q) -> [-q,q) */
+  const double   in_bias = -(4503599627370496.0 + (FWD ? 2.0 * p.q_fd : p.q_fd));
   const double   q_bias = NTT_FP_MAGIC + p.q_fd; /* lazy output: v + q lands in (0, 2q) */
   const double2 *g_fd  = (const double2 *)(FWD ? p.fwd_fd : p.inv_fd);
   const double2 *g_ct  = (const double2 *)(FWD ? p.fwd_ct_fd : p.inv_ct_fd);
@@ -368,7 +384,7 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
 #pragma unroll
         for(int b = 0; b < NB; b++)
           x[b] = fp_from_u64(*reinterpret_cast<const uint64_t *>(ring_ptr + blk_slot(b) * 4096u + off), in_bias);
-        fp_network<RA, true, false, Q50, 1>(x, c, p, [&](int t) { return tw_s[t]; });
+        fp_network_fwd<RA, FpSel<0, Q50, L, 0>>(x, c, [&](int t) { return tw_s[t]; });
 #pragma unroll
         for(int b = 0; b < NB; b++)
           *reinterpret_cast<double *>(ring_ptr + blk_slot(b) * 4096u + off) = x[b];
@@ -404,7 +420,7 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
          * (|v| < q) are final */
 #pragma unroll
         for(int cidx = 0; cidx < COLS; cidx++) {
-          fp_network<RA, false, true, Q50, 0>(x[cidx], c, p, [&](int t) { return tw_s[t]; });
+          fp_network_inv<RA, true, FpSel<1, Q50, L, 0>>(x[cidx], c, p, [&](int t) { return tw_s[t]; });
           const uint32_t j = tid + cidx * T;
 #pragma unroll
           for(int b = 0; b < NB; b++) gout[(size_t)b * 512 + j] = fp_to_u64(x[cidx][b], c, p.q);
@@ -413,7 +429,7 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
         /* strided inverse passes follow (they accept [0,2q)): fold and hand over the canonical residue */
 #pragma unroll
         for(int cidx = 0; cidx < COLS; cidx++) {
-          fp_network<RA, false, false, Q50, 0>(x[cidx], c, p, [&](int t) { return tw_s[t]; });
+          fp_network_inv<RA, false, FpSel<2, Q50, L, 0>>(x[cidx], c, p, [&](int t) { return tw_s[t]; });
           const uint32_t j = tid + cidx * T;
 #pragma unroll
           for(int b = 0; b < NB; b++) gout[(size_t)b * 512 + j] = fp_to_u64(fp_fold(x[cidx][b], c), c, p.q);
@@ -431,7 +447,8 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
 #pragma unroll
       for(int kk = 0; kk < 32; kk++)
         x[kk] = *reinterpret_cast<const double *>(base + kk * 128 + ((jc ^ (uint32_t)(kk & 7)) << 4));
-      fp_network<5, FWD, false, Q50, 0>(x, c, p, [&](int t) { return tw[t]; });
+      if constexpr(FWD) fp_network_fwd<5, FpSel<0, Q50, L, 1>>(x, c, [&](int t) { return tw[t]; });
+      else fp_network_inv<5, false, FpSel<1, Q50, L, 1>>(x, c, p, [&](int t) { return tw[t]; });
 #pragma unroll
       for(int kk = 0; kk < 32; kk++)
         *reinterpret_cast<double *>(base + kk * 128 + ((jc ^ (uint32_t)(kk & 7)) << 4)) = x[kk];
@@ -445,18 +462,23 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
 #pragma unroll
       for(int cc = 0; cc < 8; cc++) {
         const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(base + (((uint32_t)cc ^ (lane & 7u)) << 4));
-        x[2 * cc]     = FWD ? __longlong_as_double((long long)v.x) : fp_from_u64(v.x);
-        x[2 * cc + 1] = FWD ? __longlong_as_double((long long)v.y) : fp_from_u64(v.y);
+        x[2 * cc]     = FWD ? __longlong_as_double((long long)v.x) : fp_from_u64(v.x, in_bias);
+        x[2 * cc + 1] = FWD ? __longlong_as_double((long long)v.y) : fp_from_u64(v.y, in_bias);
       }
       const double2 *tw = g_ct + ((size_t)cp * NB + blk) * 32 + lane;
-      fp_network<4, FWD, false, Q50, 2>(x, c, p, [&](int t) { return __ldg(tw + (size_t)t * groups); }, [&]() {
-        /* the first block's store has had this block's loads and two stages of butterflies to drain: its slot is
-         * re-armed here without stalling the warp (the block it receives is needed by the next polynomial's pass A) */
-        if(FWD && rearm_first && lane == 0) {
-          tma_wait_read_all();
-          issue_load(g0 + warp + SLOTS);
-        }
-      });
+      auto twf = [&](int t) { return __ldg(tw + (size_t)t * groups); };
+      if constexpr(FWD) {
+        fp_network_fwd<4, FpSel<0, Q50, L, 2>>(x, c, twf, [&]() {
+          /* the first block's store has had this block's loads and two stages of butterflies to drain: its slot is
+           * re-armed here without stalling the warp (the block it receives is needed by the next polynomial's pass A) */
+          if(rearm_first && lane == 0) {
+            tma_wait_read_all();
+            issue_load(g0 + warp + SLOTS);
+          }
+        });
+      } else {
+        fp_network_inv<4, false, FpSel<1, Q50, L, 2>>(x, c, p, twf);
+      }
 #pragma unroll
       for(int cc = 0; cc < 8; cc++) {
         ulonglong2 v;

@@ -3,21 +3,29 @@
 Python floats are IEEE binary64 and `float(Fraction)` rounds to nearest-even, so fused multiply-add can be
 emulated exactly.  The tests below (no GPU needed) pin down the claims the kernel's range schedules rest on:
 
-  * fp_mul / fp_mul_wide / fp_fold return exact integers congruent to the true product / value, with the
-    stated magnitude bounds, for operands up to the limits the schedules allow -- and fp_mul really does break
-    just beyond 2^51 (which is why fp_mul_wide exists);
-  * the worst-case bound propagation of every pass shape (3, 4, 5 stages; forward, inverse, final N^-1 stage;
-    q <= 2^49 - 1024 and q <= 2^50 - 2048) stays inside those limits.
-
-The schedule model mirrors fp_network() line by line; if the kernel's schedule changes, change it here too.
+  * fp_mul (plain and coarse rounding) and fp_fold return exact integers congruent to the true product / value,
+    with the stated magnitude bounds, for operands up to the limits the schedules allow -- and the plain rounding
+    really does break just beyond 2^51 (which is why the coarse one exists);
+  * the generated schedule tables (csrc/ntt_fp_schedule.h, tools/gen_fp_schedule.py) are the ones the generator
+    produces today, and an INDEPENDENT bound propagation over those tables -- per position, exact rationals --
+    stays inside every limit for the largest moduli each schedule serves and for small ones;
+  * whole register networks, emulated instruction by instruction with the tables' fold / rounding decisions on
+    extreme inputs, produce exact integers congruent to the true butterflies.
 """
+import importlib.util
+import os
 import random
 from fractions import Fraction as F
 
 import pytest
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_spec = importlib.util.spec_from_file_location("gen_fp_schedule", os.path.join(ROOT, "tools", "gen_fp_schedule.py"))
+gen = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(gen)
+
 MAGIC = 6755399441055744.0      # 1.5 * 2^52
-T52 = 4503599627370496.0        # 2^52
+MAGIC2 = 13510798882111488.0    # 3 * 2^52
 Q49 = (1 << 49) - 1024 - 1023   # largest odd value the first schedule accepts is 2^49 - 1025; any odd q below works
 Q50 = (1 << 50) - 2049
 
@@ -32,26 +40,15 @@ def fp_fold(v, q):
     return fma(-k, qd, v)
 
 
-def fp_mul(y, w, q):
+def fp_mul(y, w, q, coarse=False):
     qd = float(q)
     winv = float(w) / qd
-    cc = fma(y, winv, MAGIC) - MAGIC
+    m = MAGIC2 if coarse else MAGIC
+    cc = fma(y, winv, m) - m
     h = y * float(w)
     l = fma(y, float(w), -h)
     d = fma(-cc, qd, h)
     return d + l, cc
-
-
-def fp_mul_wide(y, w, q):
-    qd = float(q)
-    winv = float(w) / qd
-    arg = y * winv
-    ca = (abs(arg) + T52) - T52
-    qs = -qd if (arg > 0 or (arg == 0 and str(arg)[0] != "-")) else qd
-    h = y * float(w)
-    l = fma(y, float(w), -h)
-    d = fma(ca, qs, h)
-    return d + l, ca
 
 
 def operands(q, limit_q, n, rng):
@@ -74,9 +71,9 @@ def test_fp_mul_is_exact_below_2_pow_51(q, lim):
         assert F(abs(int(t))) <= q * (F(1, 2) + F(abs(int(y)), 1 << 54))
 
 
-def test_fp_mul_breaks_beyond_2_pow_51_and_wide_does_not():
-    """A negative operand whose quotient exceeds 2^51 lands where ulp = 1/2: the magic rounding yields a
-    half-integer quotient (this is the failure found on the GPU); the 2^52 form stays exact up to 2^52."""
+def test_plain_rounding_breaks_beyond_2_pow_51_and_coarse_does_not():
+    """A negative operand whose quotient exceeds 2^51 lands where ulp = 1/2: the 1.5*2^52 constant yields a
+    half-integer quotient (the failure once seen on the GPU); the 3*2^52 constant stays exact up to 2^52."""
     q, rng = Q49, random.Random(2)
     broke = 0
     for _ in range(4000):
@@ -84,21 +81,22 @@ def test_fp_mul_breaks_beyond_2_pow_51_and_wide_does_not():
         y = -float(rng.randrange(int(4.2 * q), int(7.9 * q)))
         _, cc = fp_mul(y, w, q)
         broke += cc != int(cc)
-        t, ca = fp_mul_wide(y, w, q)
-        assert ca == int(ca) and t == int(t) and (int(t) - int(y) * w) % q == 0
-        assert abs(t) < q
+        t, ca = fp_mul(y, w, q, coarse=True)
+        assert ca == int(ca) and int(ca) % 2 == 0 and t == int(t) and (int(t) - int(y) * w) % q == 0
+        assert F(abs(int(t))) <= q * (1 + F(abs(int(y)), 1 << 54))
     assert broke > 0
 
 
 @pytest.mark.parametrize("q,lim", [(Q49, 7.99), (Q50, 3.99)])
-def test_fp_mul_wide_is_exact_below_2_pow_52(q, lim):
+def test_coarse_rounding_is_exact_below_2_pow_52(q, lim):
     rng = random.Random(3)
     assert lim * q < (1 << 52)
     for y, w in operands(q, lim, 4000, rng):
-        t, ca = fp_mul_wide(y, w, q)
-        assert ca == int(ca) and t == int(t)
+        t, ca = fp_mul(y, w, q, coarse=True)
+        assert ca == int(ca) and int(ca) % 2 == 0 and t == int(t)
         assert (int(t) - int(y) * w) % q == 0
-        assert F(abs(int(t))) <= q * (F(1, 2) + min(F(abs(int(y)), 1 << 53), F(1, 4)) + F(abs(int(y)), 1 << 54))
+        assert F(abs(int(t))) <= q * (1 + F(abs(int(y)), 1 << 54))
+        assert abs(t) < (1 << 53)
 
 
 @pytest.mark.parametrize("q", [Q49, Q50, 7681, 0x10001])
@@ -111,77 +109,168 @@ def test_fp_fold(q):
         assert abs(r) <= q / 2 + 6
 
 
-# ---- worst-case bounds of the pass schedules ----------------------------------------------------------------
+# ---- the generated schedules ---------------------------------------------------------------------------------
 
-class Schedule:
-    """Mirror of fp_network(): tracks the largest magnitude any coefficient can have (exact rationals, absolute
-    units) and checks every multiplied operand against the limit of the rounding used for it.
+@pytest.fixture(scope="module")
+def schedules():
+    return gen.all_schedules()
 
-    |fold(v)| <= q/2 + 6.  With winv = RN(w/q) (absolute error <= 2^-54 because w < q):
-      fp_mul       one fused rounding straight to an integer:   |t| <= q * (1/2 + |y| * 2^-54)
-      fp_mul_wide  RN(y*winv), then rint of that (|y| < 2^52):   |t| <= q * (1/2 + min(|y| * 2^-53, 1/4) + |y| * 2^-54)
-    """
 
-    def __init__(self, q, q50):
-        self.q, self.q50 = q, q50
-        self.fold = F(q, 2) + 6
+def test_schedule_header_is_current():
+    with open(gen.HEADER) as fh:
+        assert fh.read() == gen.render(), "run python tools/gen_fp_schedule.py"
 
-    def mul(self, operand, wide):
-        assert operand < (1 << (52 if wide else 51)), (float(operand / self.q), wide)
-        err = operand / (1 << 54)
-        if wide:
-            err += min(operand / (1 << 53), F(1, 4))
-        return self.q * (F(1, 2) + err)
 
-    def forward(self, R, b_in, role):
-        """role: 1 first pass (input centred, |v| <= 2q), 0 middle, 2 last (the caller folds afterwards)"""
-        assert b_in < (1 << 53)
-        lean = not self.q50 and role != 0
-        b = b_in if lean else self.fold
-        for u in range(R):
-            if self.q50 and R == 5 and u == 3:
-                b = self.fold
-            if self.q50:
-                wide = R == 4 and u == 3
+P51, P52, P53 = F(1 << 51), F(1 << 52), F(1 << 53)
+
+
+def check_forward(passes, q):
+    """Independent re-derivation: forward bounds are uniform; every fold mask must be all-or-nothing."""
+    b = F(2 * q)
+    fb = F(q, 2) + 6
+    for p in passes:
+        n = 1 << p.R
+        full = (1 << n) - 1
+        for s in range(p.R):
+            assert p.fold_before[s] in (0, full) and p.coarse[s] in (0, full)
+            if p.fold_before[s]:
+                assert b < P53
+                b = fb
+            if p.coarse[s]:
+                assert b < P52
+                b = b + q * (1 + b / (1 << 54))
             else:
-                wide = u >= 4 if role == 1 else (u >= 2 if role == 2 else False)
-            b = b + self.mul(b, wide)
-            assert b < (1 << 53)
-        return b
+                assert b < P51
+                b = b + q * (F(1, 2) + b / (1 << 54))
+            assert b < P53
+        assert p.fold_end == 0
+    return b
 
-    def inverse(self, R, b_in, final):
-        assert b_in < (1 << 53)
-        q50 = self.q50
-        b = self.fold
-        for u in range(R - 1, -1, -1):
-            if (R == 5 and u == 1) or (q50 and R == 4 and u == 0):
-                b = self.fold
-            since = (5 - u if u >= 2 else 2 - u) if R == 5 else (1 if (q50 and R == 4 and u == 0) else R - u)
-            wide = since >= 2 if q50 else since >= 4
-            if final and u == 0:
-                b = self.mul(2 * b, True)      # both outputs are products (of the sum and of the difference)
+
+def check_inverse_pass(p, b_in, q, final):
+    n = 1 << p.R
+    fb = F(q, 2) + 6
+    b = [F(b_in)] * n
+    for s in range(p.R):
+        d = 1 << s
+        for j in range(n):
+            if (p.fold_before[s] >> j) & 1:
+                assert b[j] < P53
+                b[j] = fb
+        nb = list(b)
+        last = final and s == p.R - 1
+        for lo in range(n):
+            if lo & d:
+                assert not (p.coarse[s] >> lo) & 1
+                continue
+            hi = lo + d
+            D = b[lo] + b[hi]
+            assert D < P53                                   # X + Y and X - Y are exact
+            if (p.coarse[s] >> lo) & 1:
+                assert D < P52 and not last
+                t = q * (1 + D / (1 << 54))
             else:
-                b = max(2 * b, self.mul(2 * b, wide))
-            assert b < (1 << 53)
-        return b
+                assert D < P51
+                t = q * (F(1, 2) + D / (1 << 54))
+            if last:
+                nb[lo] = nb[hi] = t
+            else:
+                nb[lo], nb[hi] = D, t
+        b = nb
+    for j in range(n):
+        if (p.fold_end >> j) & 1:
+            b[j] = fb
+    return max(b)
 
 
-@pytest.mark.parametrize("q,q50", [((1 << 49) - 1025, False), (Q49, False), ((1 << 49) - 1023, True), (Q50, True),
-                                   (7681, False), (0x1fffffc800001, False), (0x3ffffffef4001, True)])
-def test_range_schedules_stay_inside_their_limits(q, q50):
-    s = Schedule(q, q50)
-    for RA in (3, 4, 5):                       # L = 12, 13, 14
-        # forward: input contract [0,4q); passes A (RA stages), B (5), C (4), then a fold
-        b = s.forward(RA, 4 * q if q50 else 2 * q, 1)
-        b = s.forward(5, b, 0)
-        b = s.forward(4, b, 2)
-        assert b < (1 << 53)                   # what the final fold accepts
-        # inverse: input contract [0,2q); passes C (4), B (5), A (RA, with or without the N^-1 stage)
-        b = s.inverse(4, 2 * q, False)
-        b = s.inverse(5, b, False)
-        s.inverse(RA, b, False)
-        # the N^-1 products are converted without another fold: they must be below q in magnitude
-        assert s.inverse(RA, b, True) < q, (RA, float(s.inverse(RA, b, True) / q))
+@pytest.mark.parametrize("q50,q", [(0, (1 << 49) - 1025), (0, Q49), (0, 0x1fffffc800001), (0, 7681),
+                                   (1, (1 << 50) - 2049), (1, 0x3ffffffef4001), (1, (1 << 49) - 1023)])
+def test_schedules_stay_inside_their_limits(schedules, q50, q):
+    for L in (12, 13, 14):
+        b = check_forward(schedules[("fwd", q50, L)], q)
+        assert b < P53                                       # what the final fold accepts
+        pc, pb, pa = schedules[("inv", q50, L)]
+        pc2, pb2, pn = schedules[("invnf", q50, L)]
+        assert (pc.fold_before, pc.coarse, pc.fold_end) == (pc2.fold_before, pc2.coarse, pc2.fold_end)
+        assert (pb.fold_before, pb.coarse, pb.fold_end) == (pb2.fold_before, pb2.coarse, pb2.fold_end)
+        bc = check_inverse_pass(pc, q, q, False)             # input [0,2q) centred to [-q,q)
+        bb = check_inverse_pass(pb, bc, q, False)
+        assert check_inverse_pass(pa, bb, q, True) < q       # N^-1 products are converted without another fold
+        assert check_inverse_pass(pn, bb, q, False) < P53    # chunk of a larger transform: folded afterwards
+
+
+def emulate_inverse_pass(p, x, tw, q, final, ninv=None, ninv_w=None):
+    """The kernel's instruction sequence (fp_network_inv) on doubles; tw[(u, sub)] = twiddle of network stage u."""
+    R, n = p.R, 1 << p.R
+    for s in range(R):
+        u, d = R - 1 - s, 1 << s
+        for j in range(n):
+            if (p.fold_before[s] >> j) & 1:
+                x[j] = fp_fold(x[j], q)
+        if final and u == 0:
+            for k in range(d):
+                sm, df = x[k] + x[k + d], x[k] - x[k + d]
+                x[k], _ = fp_mul(sm, ninv, q)
+                x[k + d], _ = fp_mul(df, ninv_w, q)
+        else:
+            for sub in range(1 << u):
+                for k in range(d):
+                    lo = sub * 2 * d + k
+                    df = x[lo] - x[lo + d]
+                    x[lo] = x[lo] + x[lo + d]
+                    x[lo + d], _ = fp_mul(df, tw[(u, sub)], q, coarse=bool((p.coarse[s] >> lo) & 1))
+    for j in range(n):
+        if (p.fold_end >> j) & 1:
+            x[j] = fp_fold(x[j], q)
+    return x
+
+
+@pytest.mark.parametrize("q50,q", [(0, Q49), (1, Q50)])
+def test_inverse_networks_emulated_on_extreme_inputs(schedules, q50, q):
+    """Pass C -> B -> A (with the N^-1 stage) of the L = 14 inverse, emulated with exact FMA on inputs pinned to
+    the contract's edges: every intermediate is an integer below 2^53 and the result is congruent to the exact
+    Gentleman-Sande network."""
+    rng = random.Random(7 + q50)
+    pc, pb, pa = schedules[("inv", q50, 14)]
+    ninv, ninv_w = rng.randrange(1, q), rng.randrange(1, q)
+    for trial in range(60):
+        edge = rng.choice([q, -q, q - 1, 1 - q, None])
+        x = [float(edge if edge is not None else rng.randrange(-q, q)) for _ in range(16)]
+        exact = [int(v) for v in x]
+        tw = {(u, sub): rng.choice([1, q - 1, rng.randrange(1, q)]) for u in range(5) for sub in range(1 << u)}
+        y = emulate_inverse_pass(pc, list(x), tw, q, False)
+        for s in range(4):                                   # exact network on integers
+            u, d = 3 - s, 1 << s
+            for sub in range(1 << u):
+                for k in range(d):
+                    lo = sub * 2 * d + k
+                    a, b = exact[lo], exact[lo + d]
+                    exact[lo], exact[lo + d] = a + b, (a - b) * tw[(u, sub)]
+        for got, want in zip(y, exact):
+            assert got == int(got) and abs(got) < (1 << 53) and (int(got) - want) % q == 0
+        # the value a next-pass thread sees is any of these outputs: feed the largest ones into pass B and A
+        big = max(y, key=abs)
+        for p, final in ((pb, False), (pa, True)):
+            n = 1 << p.R
+            xin = [big if rng.random() < 0.7 else float(rng.randrange(-q // 2, q // 2)) for _ in range(n)]
+            ex = [int(v) for v in xin]
+            out = emulate_inverse_pass(p, list(xin), tw, q, final, ninv, ninv_w)
+            for s in range(p.R):
+                u, d = p.R - 1 - s, 1 << s
+                if final and u == 0:
+                    for k in range(d):
+                        a, b = ex[k], ex[k + d]
+                        ex[k], ex[k + d] = (a + b) * ninv, (a - b) * ninv_w
+                else:
+                    for sub in range(1 << u):
+                        for k in range(d):
+                            lo = sub * 2 * d + k
+                            a, b = ex[lo], ex[lo + d]
+                            ex[lo], ex[lo + d] = a + b, (a - b) * tw[(u, sub)]
+            for got, want in zip(out, ex):
+                assert got == int(got) and (int(got) - want) % q == 0
+                assert abs(got) < (q if final else (1 << 53))
+            big = max(out, key=abs) if not final else big
 
 
 def primes_below(top, step, count):
@@ -211,12 +300,11 @@ def primes_below(top, step, count):
         q -= step
 
 
-@pytest.mark.parametrize("logn,top,n_values", [(13, (1 << 49) - 1024, 16), (12, (1 << 50) - 2048, 8)])
-def test_final_stage_products_stay_below_q(logn, top, n_values):
-    """The two geometries whose last inverse stage multiplies sums of almost 2^52 (49-bit q at N = 2^13, 50-bit q
-    at N = 2^12) convert the N^-1 products without another fold, which needs |t| < q.  The bound above gives
-    that (1/2 + 1/4 + <1/4); here the worst multipliers -- N^-1 * w_inv[1] close to q -- are tried on the
-    largest moduli with operands at the top of the range."""
+@pytest.mark.parametrize("logn,top", [(13, (1 << 49) - 1024), (12, (1 << 50) - 2048), (14, (1 << 49) - 1024)])
+def test_final_stage_products_stay_below_q(logn, top):
+    """The N^-1 stage converts its products without another fold, which needs |t| < q: the schedule keeps the
+    operands of that stage below 2^51 so the plain rounding applies (|t| <= q*(1/2 + 1/8)).  The worst multipliers
+    -- N^-1 * w_inv[1] close to q -- are tried on the largest moduli with operands at the top of that range."""
     N, rng = 1 << logn, random.Random(6)
     worst = 0.0
     for q in primes_below(top, 2 * N, 40):
@@ -227,10 +315,8 @@ def test_final_stage_products_stay_below_q(logn, top, n_values):
         i = pow(x, (q - 1) // 4, q)             # a square root of -1: w_inv[1] is +-i
         for w in (ninv, ninv * i % q, ninv * (q - i) % q):
             for _ in range(300):
-                v = rng.choice([1, -1]) * ((q - 1) // 2 - rng.choice([0, 1, rng.randrange(0, 1 << 30)]))
-                s = n_values * v
-                assert abs(s) < (1 << 52)
-                t, _ = fp_mul_wide(float(s), w, q)
+                s = rng.choice([1, -1]) * ((1 << 51) - 1 - rng.choice([0, 1, rng.randrange(0, 1 << 30)]))
+                t, _ = fp_mul(float(s), w, q)
                 assert abs(t) < q and (int(t) - s * w) % q == 0
                 worst = max(worst, abs(t) / q)
-    assert worst > 0.74                          # the sample does reach the regime the bound is about
+    assert worst > 0.55                          # the sample does reach the regime the bound is about

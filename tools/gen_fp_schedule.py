@@ -1,0 +1,241 @@
+#!/usr/bin/env python
+"""Range schedules of the FP64 ring kernels (csrc/ntt_ring_fp.cuh): where values are folded and which rounding a
+product uses.  This file is the single source of truth: it derives the schedules with exact rational bounds,
+writes csrc/ntt_fp_schedule.h, and tests/test_fp64_arith_model.py imports it to re-check every bound and to make
+sure the header on disk is the one this model produces.
+
+    python tools/gen_fp_schedule.py            # rewrite the header
+    python tools/gen_fp_schedule.py --check    # exit 1 if the header is stale
+
+Arithmetic recap (see the header of ntt_ring_fp.cuh).  Coefficients are integers held in doubles, |v| < 2^53.
+For a twiddle w < q with winv = RN(w/q) (absolute error <= 2^-54) and an integer operand y:
+    plain   c = (y*winv + 1.5*2^52) - 1.5*2^52   one rounding to the nearest integer, needs |y*winv| < 2^51:
+            |t| <= q*(1/2 + |y|*2^-54)
+    coarse  c = (y*winv + 3*2^52) - 3*2^52       one rounding to the nearest EVEN integer, needs |y*winv| < 2^52:
+            |t| <= q*(1 + |y|*2^-54)
+both followed by the same exact h/l/d/t steps (6 FP64 instructions either way).  A fold is v - rint(v/q)*q,
+|result| <= q/2 + 6 for |v| < 2^53 (3 instructions).
+
+Forward (Cooley-Tukey, X' = X + t, Y' = X - t): every value of a stage has the same bound b' = b + |t|(b), so the
+schedule is per stage: plain while b < 2^51, coarse while b < 2^52, else fold everything first.
+Inverse (Gentleman-Sande, X' = X + Y, Y' = t(X - Y)): sums double but products come back small, so bounds depend
+on the POSITION inside the register network -- only a few of the 2^R values ever get large.  The schedule tracks
+one bound per position and folds exactly the positions that would break a limit (operand of a product < 2^52,
+sums < 2^53), plus the positions above a cap at the end of a pass so the next pass (whose threads regroup the
+values) can start from one uniform bound.  The caps are searched for the fewest folds.
+"""
+import os
+import sys
+from fractions import Fraction as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "optimized-number-theoretic-transform-implementations_b200", "csrc", "ntt_fp_schedule.h")
+
+P51, P52, P53 = F(1 << 51), F(1 << 52), F(1 << 53)
+QMAX = {0: (1 << 49) - 1024, 1: (1 << 50) - 2048}     # largest modulus each schedule serves
+
+
+def fold_bound(q):
+    return F(q, 2) + 6
+
+
+def t_plain(y, q):
+    if isinstance(y, float):                              # cap search: floats are enough to rank candidates
+        return q * (0.5 + y / 18014398509481984.0)
+    return q * (F(1, 2) + y / (1 << 54))
+
+
+def t_coarse(y, q):
+    if isinstance(y, float):
+        return q * (1.0 + y / 18014398509481984.0)
+    return q * (1 + y / (1 << 54))
+
+
+class Pass:
+    """One register network of R stages, in processing order.  fold_before[s] / coarse[s]: bit i set = position i
+    is folded before stage s / the butterfly whose LOWER position is i uses the coarse rounding.  fold_end: positions
+    folded after the last stage."""
+
+    def __init__(self, R):
+        self.R = R
+        self.fold_before = [0] * R
+        self.coarse = [0] * R
+        self.fold_end = 0
+        self.b_out = None
+
+    def folds(self):
+        return sum(bin(m).count("1") for m in self.fold_before) + bin(self.fold_end).count("1")
+
+
+def forward_schedule(L, q50):
+    """Passes A (L-9 stages), B (5), C (4) of the forward chunk transform; input centred to |v| <= 2q."""
+    q = QMAX[q50]
+    shapes = [L - 9, 5, 4]
+    passes = [Pass(R) for R in shapes]
+    b = F(2 * q)
+    for p in passes:
+        n = 1 << p.R
+        for s in range(p.R):
+            if b >= P52 or (b >= P51 and b + t_coarse(b, q) >= P53):
+                p.fold_before[s] = (1 << n) - 1
+                b = fold_bound(q)
+            if b < P51:
+                b = b + t_plain(b, q)
+            else:
+                p.coarse[s] = (1 << n) - 1
+                b = b + t_coarse(b, q)
+            assert b < P53
+        p.b_out = b
+    return passes
+
+
+def inverse_pass(R, b_in, q, final, cap_out):
+    """Position-aware inverse network.  Stage s (processing order) pairs positions at distance d = 2^s.
+    final: the last stage is global stage 0, BOTH outputs are products (by N^-1 and N^-1*w) and must come out
+    below q in magnitude because they are converted without another fold -> plain rounding only."""
+    n = 1 << R
+    fb = float(fold_bound(q)) if isinstance(b_in, float) else fold_bound(q)
+    b = [b_in] * n
+    p = Pass(R)
+    for s in range(R):
+        d = 1 << s
+        last = final and s == R - 1
+        lim = P51 if last else P52
+        for lo in range(n):
+            if lo & d:
+                continue
+            hi = lo + d
+            while b[lo] + b[hi] >= lim or b[lo] + b[hi] >= P53:
+                j = lo if b[lo] >= b[hi] else hi
+                if b[j] <= fb:
+                    return None                      # cannot be scheduled (does not happen for the moduli served)
+                b[j] = fb
+                p.fold_before[s] |= 1 << j
+        nb = list(b)
+        for lo in range(n):
+            if lo & d:
+                continue
+            hi = lo + d
+            D = b[lo] + b[hi]
+            if D < P51:
+                t = t_plain(D, q)
+            else:
+                t = t_coarse(D, q)
+                p.coarse[s] |= 1 << lo
+            if last:
+                nb[lo] = nb[hi] = t
+            else:
+                nb[lo], nb[hi] = D, t
+        b = nb
+    if cap_out is not None:
+        for j in range(n):
+            if b[j] > cap_out:
+                b[j] = fb
+                p.fold_end |= 1 << j
+    p.b_out = max(b)
+    return p
+
+
+def inverse_schedule(L, q50):
+    """Passes C (4 stages, input centred to |v| <= q), B (5), A (L-9 stages) in two forms: with the N^-1 stage
+    (the chunk is the whole polynomial) and without (strided passes follow; the kernel folds and converts every
+    value afterwards).  Passes C and B are shared by both forms.  The caps between the passes are chosen for the
+    fewest folds per thread (pass C runs twice per thread); the search runs on floats, the winner is then
+    re-derived with exact rationals."""
+    q = QMAX[q50]
+    best = None
+    steps = list(range(2, 33))
+    for xc in steps:
+        pc = inverse_pass(4, float(q), q, False, xc / 4 * q)
+        if pc is None:
+            continue
+        for xb in steps:
+            pb = inverse_pass(5, pc.b_out, q, False, xb / 4 * q)
+            if pb is None:
+                continue
+            pa = inverse_pass(L - 9, pb.b_out, q, True, None)
+            pn = inverse_pass(L - 9, pb.b_out, q, False, None)
+            if pa is None or pn is None or pa.b_out >= 0.999 * q or pn.b_out >= 0.999 * float(P53):
+                continue
+            cost = 2 * pc.folds() + pb.folds() + pa.folds()
+            if best is None or cost < best[0]:
+                best = (cost, xc, xb)
+    assert best is not None
+    _, xc, xb = best
+    pc = inverse_pass(4, F(q), q, False, F(xc, 4) * q)
+    pb = inverse_pass(5, pc.b_out, q, False, F(xb, 4) * q)
+    pa = inverse_pass(L - 9, pb.b_out, q, True, None)
+    pn = inverse_pass(L - 9, pb.b_out, q, False, None)
+    assert pa.b_out < q and pn.b_out < P53
+    return pc, pb, pa, pn
+
+
+def all_schedules():
+    out = {}
+    for q50 in (0, 1):
+        for L in (12, 13, 14):
+            out[("fwd", q50, L)] = forward_schedule(L, q50)
+            pc, pb, pa, pn = inverse_schedule(L, q50)
+            out[("inv", q50, L)] = [pc, pb, pa]
+            out[("invnf", q50, L)] = [pc, pb, pn]
+    return out
+
+
+def render():
+    sch = all_schedules()
+    lines = [
+        "/* csrc/ntt_fp_schedule.h -- GENERATED by tools/gen_fp_schedule.py; do not edit.",
+        " * Range schedules of the FP64 ring kernels: which positions of a register network are folded before each",
+        " * stage (processing order), which butterflies use the coarse quotient rounding, which positions are folded",
+        " * after the last stage.  Bit i = position i (for `coarse`: the butterfly whose lower position is i).",
+        " * Indexed [Q50][L-12]; passes A, B, C as in ntt_ring_fp.cuh.  tests/test_fp64_arith_model.py re-derives",
+        " * every bound with exact rationals and fails if this file is stale. */",
+        "#pragma once",
+        "#include <cstdint>",
+        "namespace nttb200 {",
+        "struct FpPass {",
+        "  uint32_t fold_before[5];",
+        "  uint32_t coarse[5];",
+        "  uint32_t fold_end;",
+        "};",
+        "struct FpSchedule {",
+        "  FpPass a, b, c;",
+        "};",
+    ]
+
+    def pass_txt(p):
+        fb = p.fold_before + [0] * (5 - p.R)
+        co = p.coarse + [0] * (5 - p.R)
+        return "{{%s}, {%s}, %s}" % (", ".join("0x%08xu" % m for m in fb), ", ".join("0x%08xu" % m for m in co),
+                                     "0x%08xu" % p.fold_end)
+
+    for kind, name in (("fwd", "FP_SCHED_FWD"), ("inv", "FP_SCHED_INV"), ("invnf", "FP_SCHED_INV_NOFINAL")):
+        lines.append("constexpr FpSchedule %s[2][3] = {" % name)
+        for q50 in (0, 1):
+            lines.append("  {")
+            for L in (12, 13, 14):
+                ps = sch[(kind, q50, L)]
+                if kind == "fwd":
+                    a, b, c = ps
+                else:
+                    c, b, a = ps
+                lines.append("    /* Q50=%d L=%d: %d folds per thread */" % (
+                    q50, L, (2 * c.folds() + b.folds() + a.folds()) if kind != "fwd" else
+                    sum(bin(m).count("1") for p in ps for m in p.fold_before) + 16 * 0))
+                lines.append("    {%s,\n     %s,\n     %s}," % (pass_txt(a), pass_txt(b), pass_txt(c)))
+            lines.append("  },")
+        lines.append("};")
+    lines.append("}  // namespace nttb200")
+    return "\n".join(lines) + "\n"
+
+
+if __name__ == "__main__":
+    txt = render()
+    if "--check" in sys.argv:
+        ok = os.path.exists(HEADER) and open(HEADER).read() == txt
+        print("ntt_fp_schedule.h is %s" % ("up to date" if ok else "STALE"))
+        sys.exit(0 if ok else 1)
+    with open(HEADER, "w") as fh:
+        fh.write(txt)
+    for k, ps in sorted(all_schedules().items()):
+        print(k, [(p.R, p.folds(), float(p.b_out / QMAX[k[1]])) for p in ps])
