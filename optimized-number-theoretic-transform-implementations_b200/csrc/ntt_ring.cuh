@@ -49,6 +49,10 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+/* Plain try_wait loop.  A suspend-time hint (the form with a third operand) was measured and does not pay: the
+ * inverse kernel spends about 340 instructions per thread and polynomial polling (TRYWAIT, BRA, YIELD), but they
+ * are issued by warps that have nothing else to do, and with the hint both kernels were 0.3 % slower
+ * (profiles/r02_kernel_experiments.txt). */
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
   asm volatile(
@@ -131,6 +135,13 @@ struct RingCfg {
   static constexpr int BOXB     = NB / 4;
   static constexpr int SLOTS    = ((BUDGET - TW_BYTES - 1024 - 128) / 4096) / (NB / 2) * (NB / 2); /* 48 / 24 / 12 for L = 14 / 13 / 12 */
   static constexpr int SMEM     = SLOTS * 4096 + 1024 /* alignment slack */ + TW_BYTES + 128 /* 8 load barriers + the CTA barrier */;
+  /* FP64 kernel: 16-byte twiddle entries; at L = 14 the cache also holds the FIRST-stage twiddle of pass C for every
+   * 16-coefficient group (NB*32 entries), so that the last pass starts from shared memory while its other 14
+   * per-thread twiddles are still on their way from L2 */
+  static constexpr int NTW_C0      = (L == 14) ? NB * 32 : 0;
+  static constexpr int TW_BYTES_FP = (((NTW + NTW_C0) * 16 + 127) / 128) * 128 > TW_BYTES ? (((NTW + NTW_C0) * 16 + 127) / 128) * 128 : TW_BYTES;
+  static constexpr int SMEM_FP     = SLOTS * 4096 + 1024 + TW_BYTES_FP + 128;
+  static_assert(SMEM_FP <= BUDGET, "FP64 ring kernel: shared memory budget");
   static_assert(SLOTS > NB && 4 * NB > SLOTS && SLOTS % BOXB == 0, "ring depth vs. mbarrier reuse distance");
   static_assert(SLOTS % (NB / 2) == 0, "half a polynomial must not wrap around the ring (blk_slot)");
 };

@@ -269,7 +269,12 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
   const uint32_t ring     = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t *      ring_ptr = smem_raw + (ring - smem_u32(smem_raw));
   double2 *      tw_s     = reinterpret_cast<double2 *>(ring_ptr + SLOTS * 4096); /* NTW x 16 bytes */
-  const uint32_t bars     = ring + SLOTS * 4096 + C::TW_BYTES;
+  const uint32_t bars     = ring + SLOTS * 4096 + C::TW_BYTES_FP;
+#ifdef NTT_NO_TWC0
+  constexpr bool TWC0 = false;
+#else
+  constexpr bool TWC0 = FWD && C::NTW_C0 > 0; /* pass C's first-stage twiddles come from shared memory */
+#endif
   const uint32_t cta_bar  = bars + 8u * (2u * C::NBAR);
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -343,6 +348,9 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
         }
         const uint32_t u = 31u - __clz(t + 1u), sub = t + 1u - (1u << u);
         tw_s[e] = __ldg(g_fd + (((size_t)1 << (st + u)) + ((size_t)blk << u) + sub));
+      }
+      if constexpr(TWC0) {
+        for(uint32_t e = tid; e < (uint32_t)C::NTW_C0; e += T) tw_s[C::NTW + e] = __ldg(g_ct + (size_t)cp * NB * 32 + e);
       }
       cached_cp = cp;
       __syncthreads();
@@ -466,7 +474,8 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
         x[2 * cc + 1] = FWD ? __longlong_as_double((long long)v.y) : fp_from_u64(v.y, in_bias);
       }
       const double2 *tw = g_ct + ((size_t)cp * NB + blk) * 32 + lane;
-      auto twf = [&](int t) { return __ldg(tw + (size_t)t * groups); };
+      const double2 *tw0 = tw_s + C::NTW + blk * 32 + lane;
+      auto           twf = [&](int t) { return (TWC0 && t == 0) ? *tw0 : __ldg(tw + (size_t)t * groups); };
       if constexpr(FWD) {
         fp_network_fwd<4, FpSel<0, Q50, L, 2>>(x, c, twf, [&]() {
           /* the first block's store has had this block's loads and two stages of butterflies to drain: its slot is

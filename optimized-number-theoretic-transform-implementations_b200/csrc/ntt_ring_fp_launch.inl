@@ -12,10 +12,10 @@ static int ring_fp_launch_one(int device, const ntt_cuda_params_t &p, const CUte
   auto        kern      = k_ring_fp<L, FWD, MODE, Q50>;
   static bool ready[64] = {false};
   if(!ready[device & 63]) {
-    NL_CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    NL_CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_FP));
     ready[device & 63] = true;
   }
-  kern<<<grid, C::THREADS, C::SMEM, st>>>(p, tm, tm2, n_chunks, d_a, o.d_other, o.other_mask);
+  kern<<<grid, C::THREADS, C::SMEM_FP, st>>>(p, tm, tm2, n_chunks, d_a, o.d_other, o.other_mask);
   NL_CU(cudaGetLastError());
   return 0;
 }
@@ -23,6 +23,14 @@ static int ring_fp_launch_one(int device, const ntt_cuda_params_t &p, const CUte
 #define NTT_RING_CAT2(a, b) a##b
 #define NTT_RING_CAT(a, b) NTT_RING_CAT2(a, b)
 
+#if defined(NTT_EXPERIMENT) && NTT_RING_L != 14
+/* -DNTT_EXPERIMENT: scratch builds for kernel A/B timing (tools/exp_build.sh) carry the L = 14 kernels only */
+int NTT_RING_CAT(ring_fp_launch_, NTT_RING_L)(bool, int, const ntt_cuda_params_t &, uint64_t *, size_t, cudaStream_t,
+                                              const RingOpts &)
+{
+  return nl_fail_msg("experiment build: only the L = 14 FP64 ring kernels are compiled");
+}
+#else
 int NTT_RING_CAT(ring_fp_launch_, NTT_RING_L)(bool fwd, int device, const ntt_cuda_params_t &p, uint64_t *d_a,
                                               size_t n_chunks, cudaStream_t st, const RingOpts &o)
 {
@@ -37,6 +45,11 @@ int NTT_RING_CAT(ring_fp_launch_, NTT_RING_L)(bool fwd, int device, const ntt_cu
   if(mc && grid * mc > n_chunks) grid = (n_chunks + mc - 1) / mc;
   const bool     q50 = p.fp64 == 2; /* 50-bit range schedule */
   const unsigned g   = (unsigned)grid;
+#ifdef NTT_EXPERIMENT
+  (void)q50;
+  return fwd ? ring_fp_launch_one<L, true, RING_PLAIN, false>(device, p, tm, tm2, g, d_a, n_chunks, st, o)
+             : ring_fp_launch_one<L, false, RING_PLAIN, false>(device, p, tm, tm2, g, d_a, n_chunks, st, o);
+#else
   if(!fwd) {
     return q50 ? ring_fp_launch_one<L, false, RING_PLAIN, true>(device, p, tm, tm2, g, d_a, n_chunks, st, o)
                : ring_fp_launch_one<L, false, RING_PLAIN, false>(device, p, tm, tm2, g, d_a, n_chunks, st, o);
@@ -51,7 +64,9 @@ int NTT_RING_CAT(ring_fp_launch_, NTT_RING_L)(bool fwd, int device, const ntt_cu
   }
   return q50 ? ring_fp_launch_one<L, true, RING_PLAIN, true>(device, p, tm, tm2, g, d_a, n_chunks, st, o)
              : ring_fp_launch_one<L, true, RING_PLAIN, false>(device, p, tm, tm2, g, d_a, n_chunks, st, o);
+#endif
 }
+#endif
 
 }  // namespace nttb200
 
