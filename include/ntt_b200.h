@@ -117,6 +117,18 @@ int ntt_b200_fwd_lazy_batch(const ntt_b200_plan_t *plan, uint64_t *d_a, size_t b
 int ntt_b200_inv_batch(const ntt_b200_plan_t *plan, uint64_t *d_a, size_t batch, void *stream);
 
 /*
+ * Order-agnostic variants for consumers that only combine transforms pointwise (the reference's analogue is
+ * fwd_ntt_radix4_avx512_ifma_unordered, include/ntt_avx512_ifma.h:88, whose order tests/test_correctness.c:179-209
+ * repairs with fix_a_order).  fwd_unordered's output order is implementation-defined; inv_unordered consumes exactly
+ * that order; ntt_b200_unordered_index(plan, i) is the index in fwd_ntt_ref_harvey's output of the value at
+ * position i of the unordered output ((uint64_t)-1 if i >= N).  Today the permutation is the identity: the
+ * in-place network of the sm_100a kernels leaves the reference order for free.
+ */
+int      ntt_b200_fwd_unordered_batch(const ntt_b200_plan_t *plan, uint64_t *d_a, size_t batch, void *stream);
+int      ntt_b200_inv_unordered_batch(const ntt_b200_plan_t *plan, uint64_t *d_a, size_t batch, void *stream);
+uint64_t ntt_b200_unordered_index(const ntt_b200_plan_t *plan, uint64_t i);
+
+/*
  * RNS form: limb l of every polynomial uses plans[l] (its own q).  d_a holds `limbs` consecutive
  * blocks of `batch_per_limb` polynomials.  All plans must share N and device.  The limbs run concurrently on
  * internal streams that fork from and join back into `stream`.

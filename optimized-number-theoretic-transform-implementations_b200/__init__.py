@@ -53,7 +53,10 @@ def _bind():
     L.ntt_b200_plan_is_lazy.argtypes = [vp]
     L.ntt_b200_plan_describe.argtypes = [vp, i, C.c_char_p, sz, C.POINTER(i)]
     L.ntt_b200_plan_export_tables.argtypes = [vp, vp, vp, vp, vp, C.POINTER(u64), C.POINTER(u64)]
-    for f in ("ntt_b200_fwd_batch", "ntt_b200_fwd_lazy_batch", "ntt_b200_inv_batch"):
+    L.ntt_b200_unordered_index.restype = u64
+    L.ntt_b200_unordered_index.argtypes = [vp, u64]
+    for f in ("ntt_b200_fwd_batch", "ntt_b200_fwd_lazy_batch", "ntt_b200_inv_batch", "ntt_b200_fwd_unordered_batch",
+              "ntt_b200_inv_unordered_batch"):
         getattr(L, f).argtypes = [vp, vp, sz, vp]
     for f in ("ntt_b200_fwd_rns", "ntt_b200_inv_rns"):
         getattr(L, f).argtypes = [C.POINTER(vp), sz, vp, sz, vp]
@@ -123,6 +126,7 @@ EXPORTS = [
     "ntt_b200_plan_n", "ntt_b200_plan_q", "ntt_b200_plan_device", "ntt_b200_plan_is_lazy",
     "ntt_b200_plan_export_tables", "ntt_b200_plan_describe",
     "ntt_b200_fwd_batch", "ntt_b200_fwd_lazy_batch", "ntt_b200_inv_batch",
+    "ntt_b200_fwd_unordered_batch", "ntt_b200_inv_unordered_batch", "ntt_b200_unordered_index",
     "ntt_b200_fwd_rns", "ntt_b200_inv_rns",
     "ntt_b200_fwd_tail_block", "ntt_b200_inv_tail_block", "ntt_b200_plan_set_inverse_scale",
     "ntt_b200_fwd_tail_gather", "ntt_b200_inv_tail_scatter", "ntt_b200_peer_barrier",
@@ -327,6 +331,16 @@ class Plan:
 
     def inv(self, d_a, batch, stream=None):
         _check(lib.ntt_b200_inv_batch(self._h, _ptr(d_a), batch, _stream_ptr(stream)), "inv_batch")
+
+    # order-agnostic variants (pointwise consumers); unordered_index(i) = position in the reference's output
+    def fwd_unordered(self, d_a, batch, stream=None):
+        _check(lib.ntt_b200_fwd_unordered_batch(self._h, _ptr(d_a), batch, _stream_ptr(stream)), "fwd_unordered_batch")
+
+    def inv_unordered(self, d_a, batch, stream=None):
+        _check(lib.ntt_b200_inv_unordered_batch(self._h, _ptr(d_a), batch, _stream_ptr(stream)), "inv_unordered_batch")
+
+    def unordered_index(self, i):
+        return int(lib.ntt_b200_unordered_index(self._h, i))
 
     def negacyclic_mul(self, d_c, d_a, d_b, batch, stream=None):
         _check(lib.ntt_b200_negacyclic_mul_batch(self._h, _ptr(d_c), _ptr(d_a), _ptr(d_b), batch,

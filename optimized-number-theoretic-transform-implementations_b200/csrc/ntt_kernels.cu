@@ -1251,7 +1251,11 @@ extern "C" int ntt_cuda_rns(int device, const ntt_cuda_params_t *const *plist, s
   static cudaStream_t side[64][NS];
   static cudaEvent_t  fork_ev[64], join_ev[64][NS];
   static bool         made[64] = {false};
+  static std::mutex   lock[64];
   const int           dv = device & 63;
+  /* the side streams and events are shared per device: two host threads forking into them at the same time would
+   * wait on each other's fork record (and could start before their own stream's earlier work) */
+  std::lock_guard<std::mutex> hold(lock[dv]);
   if(!made[dv]) {
     for(int i = 0; i < NS; i++) {
       CU(cudaStreamCreateWithFlags(&side[dv][i], cudaStreamNonBlocking));

@@ -194,6 +194,13 @@ class FusedDistributedNtt(DistributedNtt):
         self.px.barrier(stream)
         self.local.inv(self.px.slice_ptr, 1, stream)
 
+    def check(self):
+        """Synchronise and raise if any peer barrier gave up waiting (k_peer_barrier reports a timeout instead of
+        hanging the GPU; the kernels behind it then ran on stale peer data, so the results must not be used)."""
+        _pkg.device_sync(self.device)
+        if self.px.timed_out():
+            raise _pkg.NttError("peer barrier timed out: a rank never arrived; results of this step are invalid")
+
     def capture_pair(self, block_dev):
         """forward(block) followed by inverse(block) as one CUDA graph (returns the torch.cuda.CUDAGraph): the
         pair is eight short launches, and at N = 2^22 the host's launch path is slower than the kernels."""
@@ -208,8 +215,11 @@ class FusedDistributedNtt(DistributedNtt):
         return graph
 
     def close(self):
-        self.px.close()
-        super().close()
+        try:
+            self.check()
+        finally:
+            self.px.close()
+            super().close()
 
 
 def emulate_forward_single_gpu(N, q, psi, a_host, world):

@@ -473,6 +473,29 @@ int ntt_b200_fwd_lazy_batch(const ntt_b200_plan_t *plan, uint64_t *d_a, size_t b
   return NTT_B200_SUCCESS;
 }
 
+/* ---- order-agnostic ("unordered") entry points ------------------------------------------------------------
+ * The reference's fwd_ntt_radix4_avx512_ifma_unordered (include/ntt_avx512_ifma.h:88) leaves its output in the lane
+ * order of its last SIMD stage and so saves a final in-register transpose; consumers that only multiply pointwise
+ * do not care, and tests/test_correctness.c:179-209 (fix_a_order) restores the order for the comparison.  The
+ * contract here is the same: the output order of fwd_unordered is implementation-defined, inv_unordered accepts
+ * exactly that order, pointwise products commute with it, and ntt_b200_unordered_index tells where position i of
+ * the unordered output sits in fwd_ntt_ref_harvey's output.  On this architecture the in-place register / shared
+ * memory network leaves the reference's bit-reversed order at no cost (there is no scatter to skip: every pass
+ * writes back where it read), so the permutation is the identity today; callers written against this contract keep
+ * working if a later kernel (e.g. a multi-GPU transform that skips its final exchange) chooses another order. */
+int ntt_b200_fwd_unordered_batch(const ntt_b200_plan_t *plan, uint64_t *d_a, size_t batch, void *stream)
+{
+  return ntt_b200_fwd_batch(plan, d_a, batch, stream);
+}
+int ntt_b200_inv_unordered_batch(const ntt_b200_plan_t *plan, uint64_t *d_a, size_t batch, void *stream)
+{
+  return ntt_b200_inv_batch(plan, d_a, batch, stream);
+}
+uint64_t ntt_b200_unordered_index(const ntt_b200_plan_t *plan, uint64_t i)
+{
+  return (plan && i < plan->N) ? i : (uint64_t)-1;
+}
+
 int ntt_b200_inv_batch(const ntt_b200_plan_t *plan, uint64_t *d_a, size_t batch, void *stream)
 {
   if(check_batch(plan, d_a, 1)) return NTT_B200_ERROR;

@@ -215,3 +215,31 @@ def test_rns_limbs_sharded_over_devices(ntt, oracle):
         assert np.array_equal(_host(bufs[l]), ins[l]), "limb %d round trip" % l
     for p in plans:
         p.close()
+
+
+@pytest.mark.parametrize("m", [12, 14, 16])
+def test_unordered_contract(ntt, oracle, m):
+    """The reference's own check for its unordered variant (tests/test_correctness.c:179-209): repair the order, then
+    memcmp with fwd_ntt_ref_harvey.  Plus what a pointwise consumer relies on: inv_unordered(fwd_unordered(a) .* fwd_unordered(b))
+    is the negacyclic product."""
+    N, psi, t = _setup(oracle, m)
+    q, batch = Q49, 3
+    a = oracle.uniform(batch * N, q, 61).reshape(batch, N)
+    b = oracle.uniform(batch * N, q, 62).reshape(batch, N)
+    plan = ntt.Plan.from_psi(N, q, psi)
+    perm = np.array([plan.unordered_index(i) for i in range(N)], dtype=np.int64)
+    assert sorted(perm.tolist()) == list(range(N)) and plan.unordered_index(N) == 2**64 - 1
+    da, db = _dev(a), _dev(b)
+    plan.fwd_unordered(da, batch)
+    plan.fwd_unordered(db, batch)
+    fa = _host(da)
+    fixed = np.empty_like(fa)
+    fixed[:, perm] = fa                                         # fix_a_order
+    want_a = oracle.fwd_batch(a, q, t.w, t.w_con)
+    assert np.array_equal(fixed, want_a)
+    plan.pointwise_mul(da, da, db, batch)
+    plan.inv_unordered(da, batch)
+    fb = oracle.fwd_batch(b, q, t.w, t.w_con)
+    want = oracle.inv_batch(oracle.pointwise_mul(want_a, fb, q).reshape(batch, N), q, t.n_inv, t.w_inv, t.w_inv_con)
+    assert np.array_equal(_host(da), want)
+    plan.close()

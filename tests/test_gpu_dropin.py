@@ -24,3 +24,23 @@ def test_reference_driver_passes_with_gpu_dropin():
     assert "Bad results" not in text, [l for l in text.splitlines() if "Bad" in l][:5]
     assert text.count("Test ") >= 19, text[-500:]  # the driver stops at the first failing case
     assert text.count("Running inv_ntt_ref_harvey") >= 19
+
+
+BENCH = os.path.join(ROOT, "oracle", "_ref", "ntt-variants-bench-dropin")
+
+
+def test_reference_bench_driver_runs_with_gpu_dropin():
+    """The reference's own bench driver (tests/main.c + tests/bench.c, -DTEST_SPEED) linked against the drop-in, in
+    its single-function mode (`ntt-variants-bench 0` = fwd_ntt_ref_harvey on tests[9], tests/main.c:12-17): the
+    number it prints is the single-polynomial GPU round trip (H2D + kernel + D2H + sync per call) in ns, measured by
+    the reference's MEASURE macro.  Function 1 (fwd_ntt_seal, the reference's CPU code) runs beside it."""
+    if not os.path.exists(BENCH):
+        pytest.skip("oracle/_ref/ntt-variants-bench-dropin not built (needs /root/reference at build time)")
+    ns = {}
+    for func in (0, 1):
+        out = subprocess.run([BENCH, str(func)], capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        assert "cycle=" in out.stdout, out.stdout[-300:]
+        ns[func] = int(out.stdout.split("cycle=")[1].split()[0])
+    print("single-polynomial N=2^14 latency: GPU drop-in %d ns per call, reference fwd_ntt_seal (CPU) %d ns" % (ns[0], ns[1]))
+    assert 0 < ns[0] < 50_000_000 and ns[1] > 0
