@@ -481,6 +481,41 @@ def run_config5(ntt, torch, dist, rank, world, local):
     ok_rt = ok_rt and bool(np.array_equal(fused.px.read_slice(), a[rank::world])) and not fused.px.timed_out()
     del graph
     fused.close()
+
+    # the same exchange with a BATCH of transforms per launch / barrier: the single transform is latency-bound
+    # (32 MB over 8 GPUs), a batch amortises the launches and the barrier and fills the SMs
+    B = 8
+    ab = np.stack([a] + [splitmix64_mod(N, q, 40 + i) for i in range(1, B)])
+    fb = fs.FusedDistributedNtt(N, q, psi, rank, world, local, dist, batch=B)
+    fb.px.load_slice(np.ascontiguousarray(ab[:, rank::world]).reshape(-1))
+    blocks = torch.empty(B * (N // world), dtype=torch.int64, device="cuda")
+    fb.forward(blocks)
+    torch.cuda.synchronize()
+    first = blocks[:N // world].clone()                      # polynomial 0 of the batch is `a`
+    gathered = [torch.empty_like(first) for _ in range(world)] if rank == 0 else None
+    dist.gather(first, gathered, dst=0)
+    ok_batched = None
+    if rank == 0:
+        ok_batched = bool(np.array_equal(torch.cat(gathered).cpu().numpy().view(np.uint64), want))
+    fb.inverse(blocks)
+    torch.cuda.synchronize()
+    ok_rt = ok_rt and bool(np.array_equal(fb.px.read_slice(), np.ascontiguousarray(ab[:, rank::world]).reshape(-1)))
+
+    def step_batched():
+        fb.forward(blocks)
+        fb.inverse(blocks)
+    dist.barrier()
+    out["peer_fused_batch%d_ms_per_pair_per_polynomial" % B] = reduce_ms(timed_ms(torch, step_batched, steps)) / B
+    ok_rt = ok_rt and not fb.px.timed_out()
+    fb.close()
+    single_b = ntt.Plan.from_psi(N, q, psi, device=local)
+    dsb = torch.from_numpy(ab.view(np.int64)).cuda()
+    out["one_gpu_batch%d_ms_per_pair_per_polynomial" % B] = reduce_ms(
+        timed_ms(torch, lambda: (single_b.fwd(dsb, B), single_b.inv(dsb, B)), steps)) / B
+    single_b.close()
+    out["batched_speedup_over_one_gpu"] = (out["one_gpu_batch%d_ms_per_pair_per_polynomial" % B]
+                                           / out["peer_fused_batch%d_ms_per_pair_per_polynomial" % B])
+    out["forward_blocks_equal_oracle_peer_fused_batched"] = ok_batched
     bad = torch.tensor([0.0 if ok_rt else 1.0], device="cuda")
     dist.all_reduce(bad, op=dist.ReduceOp.MAX)
     best = min(out["peer_fused_ms_per_pair"], out["peer_fused_graph_ms_per_pair"])

@@ -200,6 +200,13 @@ int ntt_b200_fwd_tail_gather(const ntt_b200_plan_t *plan, uint64_t *const *peer_
                              uint32_t log2_parts, uint32_t rank, void *stream);
 int ntt_b200_inv_tail_scatter(const ntt_b200_plan_t *plan, uint64_t *const *peer_slices, uint64_t *d_block,
                               uint32_t log2_parts, uint32_t rank, void *stream);
+/* The same for `batch` transforms at once: every slice buffer holds `batch` slices of N/G words one after the
+ * other, d_block `batch` blocks; one launch and one barrier serve the whole batch (a single N = 2^22 exchange is
+ * latency-bound). */
+int ntt_b200_fwd_tail_gather_batch(const ntt_b200_plan_t *plan, uint64_t *const *peer_slices, uint64_t *d_block,
+                                   uint32_t log2_parts, uint32_t rank, size_t batch, void *stream);
+int ntt_b200_inv_tail_scatter_batch(const ntt_b200_plan_t *plan, uint64_t *const *peer_slices, uint64_t *d_block,
+                                    uint32_t log2_parts, uint32_t rank, size_t batch, void *stream);
 int ntt_b200_peer_barrier(int device, void *const *peer_flags, void *my_flags, uint32_t rank, uint32_t world,
                           uint32_t epoch, int *d_timed_out, void *stream);
 int ntt_b200_ipc_export(int device, void *d_ptr, void *handle64);

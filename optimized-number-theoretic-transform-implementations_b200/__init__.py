@@ -64,6 +64,8 @@ def _bind():
         getattr(L, f).argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp]
     for f in ("ntt_b200_fwd_tail_gather", "ntt_b200_inv_tail_scatter"):
         getattr(L, f).argtypes = [vp, C.POINTER(vp), vp, C.c_uint32, C.c_uint32, vp]
+    for f in ("ntt_b200_fwd_tail_gather_batch", "ntt_b200_inv_tail_scatter_batch"):
+        getattr(L, f).argtypes = [vp, C.POINTER(vp), vp, C.c_uint32, C.c_uint32, sz, vp]
     L.ntt_b200_peer_barrier.argtypes = [i, C.POINTER(vp), vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp]
     L.ntt_b200_ipc_export.argtypes = [i, vp, C.c_char_p]
     L.ntt_b200_ipc_open.argtypes = [i, C.c_char_p, C.POINTER(vp)]
@@ -130,6 +132,7 @@ EXPORTS = [
     "ntt_b200_fwd_rns", "ntt_b200_inv_rns",
     "ntt_b200_fwd_tail_block", "ntt_b200_inv_tail_block", "ntt_b200_plan_set_inverse_scale",
     "ntt_b200_fwd_tail_gather", "ntt_b200_inv_tail_scatter", "ntt_b200_peer_barrier",
+    "ntt_b200_fwd_tail_gather_batch", "ntt_b200_inv_tail_scatter_batch",
     "ntt_b200_ipc_export", "ntt_b200_ipc_open", "ntt_b200_ipc_close",
     "ntt_b200_negacyclic_mul_batch", "ntt_b200_pointwise_mul_batch",
     "ntt_b200_fwd_batch_host", "ntt_b200_inv_batch_host",
@@ -360,13 +363,13 @@ class Plan:
                "inv_tail_block")
 
     # the same, fused with the exchange over peer memory: peer_slices = ctypes array of G device pointers
-    def fwd_tail_gather(self, peer_slices, d_block, log2_parts, rank, stream=None):
-        _check(lib.ntt_b200_fwd_tail_gather(self._h, peer_slices, _ptr(d_block), log2_parts, rank,
-                                            _stream_ptr(stream)), "fwd_tail_gather")
+    def fwd_tail_gather(self, peer_slices, d_block, log2_parts, rank, stream=None, batch=1):
+        _check(lib.ntt_b200_fwd_tail_gather_batch(self._h, peer_slices, _ptr(d_block), log2_parts, rank, batch,
+                                                  _stream_ptr(stream)), "fwd_tail_gather")
 
-    def inv_tail_scatter(self, peer_slices, d_block, log2_parts, rank, stream=None):
-        _check(lib.ntt_b200_inv_tail_scatter(self._h, peer_slices, _ptr(d_block), log2_parts, rank,
-                                             _stream_ptr(stream)), "inv_tail_scatter")
+    def inv_tail_scatter(self, peer_slices, d_block, log2_parts, rank, stream=None, batch=1):
+        _check(lib.ntt_b200_inv_tail_scatter_batch(self._h, peer_slices, _ptr(d_block), log2_parts, rank, batch,
+                                                   _stream_ptr(stream)), "inv_tail_scatter")
 
     def set_inverse_scale(self, scale):
         _check(lib.ntt_b200_plan_set_inverse_scale(self._h, scale), "plan_set_inverse_scale")

@@ -126,7 +126,7 @@ int ntt_cuda_tail(int device, const ntt_cuda_params_t *p, uint64_t *d_block, uin
 /* the same tail stages fused with the exchange: forward gathers group members from the peers' slices
  * (peer_slices[p], p < 2^glog, device pointers valid on this device), inverse scatters them back */
 int ntt_cuda_tail_peer(int device, const ntt_cuda_params_t *p, uint64_t *const *peer_slices, uint64_t *d_block,
-                       uint32_t glog, uint32_t rank, int inverse, void *stream);
+                       uint32_t glog, uint32_t rank, size_t batch, int inverse, void *stream);
 /* GPU-timeline barrier over peer memory; peer_flags[k] = rank k's array of `world` uint32 flags */
 int ntt_cuda_peer_barrier(int device, void *const *peer_flags, void *my_flags, uint32_t rank, uint32_t world,
                           uint32_t epoch, int *d_timed_out, void *stream);

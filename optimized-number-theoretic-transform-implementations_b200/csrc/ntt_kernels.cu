@@ -1083,29 +1083,37 @@ __device__ __forceinline__ void st_sys(uint64_t *a, uint64_t v)
   asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(a), "l"(v) : "memory");
 }
 
+/* batch > 1: every slice buffer holds `batch` slices of N/G words one after the other and d_block `batch` blocks;
+ * one launch (and one barrier) then serves the whole batch -- at N = 2^22 the exchange of a single polynomial is
+ * latency-bound, a batch amortises the launches and the barrier. */
 template <int R, bool FWD, bool EXACT>
 __global__ void __launch_bounds__(256) k_tail_peer(const __grid_constant__ ntt_cuda_params_t p,
                                                    const __grid_constant__ PeerPtrs peers, uint64_t *__restrict__ block,
-                                                   uint32_t rank, size_t piece)
+                                                   uint32_t rank, uint32_t piece_log, size_t total)
 {
-  constexpr int  n  = 1 << R;
-  const uint32_t s0 = p.logn - R;
-  for(size_t kk = (size_t)blockIdx.x * blockDim.x + threadIdx.x; kk < piece; kk += (size_t)gridDim.x * blockDim.x) {
-    const size_t src = (size_t)rank * piece + kk; /* index in every slice = global group index of this block */
+  constexpr int  n       = 1 << R;
+  const uint32_t s0      = p.logn - R;
+  const size_t   piece   = (size_t)1 << piece_log;
+  const uint32_t loc_log = p.logn - R; /* log2 words of one slice / one block */
+  for(size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = t >> piece_log, kk = t & (piece - 1);
+    const size_t grp = (size_t)rank * piece + kk;        /* global group index of this block = index in every slice */
+    const size_t src = (b << loc_log) + grp;
+    uint64_t *   dst = block + (b << loc_log) + (kk << R);
     uint64_t     x[n];
     if(FWD) {
 #pragma unroll
       for(int k = 0; k < n; k++) x[k] = ld_sys(peers.p[k] + src);
     } else {
 #pragma unroll
-      for(int k = 0; k < n; k++) x[k] = block[(kk << R) + k];
+      for(int k = 0; k < n; k++) x[k] = dst[k];
     }
-    radix_network<R, FWD, EXACT>(x, p, s0, (uint32_t)src);
+    radix_network<R, FWD, EXACT>(x, p, s0, (uint32_t)grp);
 #pragma unroll
     for(int k = 0; k < n; k++) {
       uint64_t v = x[k];
       if(FWD) {
-        block[(kk << R) + k] = finish<EXACT>(v, p);
+        dst[k] = finish<EXACT>(v, p);
       } else {
         if(!EXACT) {
           const Red rc{p.q, p.negq, p.red_shift, p.red_mu};
@@ -1119,19 +1127,22 @@ __global__ void __launch_bounds__(256) k_tail_peer(const __grid_constant__ ntt_c
 
 template <int R, bool FWD, bool EXACT>
 static int launch_tail_peer(int device, const ntt_cuda_params_t &p, const PeerPtrs &pp, uint64_t *d_block, uint32_t rank,
-                            size_t piece, cudaStream_t st)
+                            uint32_t piece_log, size_t batch, cudaStream_t st)
 {
-  size_t       grid = (piece + 255) / 256;
-  const size_t cap  = (size_t)sm_count(device) * 8;
+  const size_t total = batch << piece_log;
+  size_t       grid  = (total + 255) / 256;
+  const size_t cap   = (size_t)sm_count(device) * 8;
   if(grid > cap) grid = cap;
-  k_tail_peer<R, FWD, EXACT><<<(unsigned)grid, 256, 0, st>>>(p, pp, d_block, rank, piece);
+  k_tail_peer<R, FWD, EXACT><<<(unsigned)grid, 256, 0, st>>>(p, pp, d_block, rank, piece_log, total);
   CU(cudaGetLastError());
   return 0;
 }
 
 extern "C" int ntt_cuda_tail_peer(int device, const ntt_cuda_params_t *p_in, uint64_t *const *peer_slices,
-                                  uint64_t *d_block, uint32_t glog, uint32_t rank, int inverse, void *stream)
+                                  uint64_t *d_block, uint32_t glog, uint32_t rank, size_t batch, int inverse,
+                                  void *stream)
 {
+  if(batch == 0) return 0;
   DevGuard g(device);
   if(!g.ok) return fail_msg("cudaSetDevice failed");
   if(glog < 1 || glog > 5 || 2 * glog > p_in->logn || rank >= (1u << glog)) return fail_msg("bad tail geometry");
@@ -1145,15 +1156,15 @@ extern "C" int ntt_cuda_tail_peer(int device, const ntt_cuda_params_t *p_in, uin
     if(!peer_slices[k]) return fail_msg("peer slice pointer is NULL");
     pp.p[k] = peer_slices[k];
   }
-  const size_t piece = (size_t)1 << (p->logn - 2 * glog);
-  cudaStream_t st    = (cudaStream_t)stream;
+  const uint32_t piece = p->logn - 2 * glog; /* log2 groups per block */
+  cudaStream_t   st    = (cudaStream_t)stream;
 #define TAILPEER(R)                                                                                                   \
   case R:                                                                                                             \
     if(p->lazy)                                                                                                       \
-      return inverse ? launch_tail_peer<R, false, false>(device, *p, pp, d_block, rank, piece, st)                    \
-                     : launch_tail_peer<R, true, false>(device, *p, pp, d_block, rank, piece, st);                    \
-    return inverse ? launch_tail_peer<R, false, true>(device, *p, pp, d_block, rank, piece, st)                       \
-                   : launch_tail_peer<R, true, true>(device, *p, pp, d_block, rank, piece, st);
+      return inverse ? launch_tail_peer<R, false, false>(device, *p, pp, d_block, rank, piece, batch, st)             \
+                     : launch_tail_peer<R, true, false>(device, *p, pp, d_block, rank, piece, batch, st);             \
+    return inverse ? launch_tail_peer<R, false, true>(device, *p, pp, d_block, rank, piece, batch, st)                \
+                   : launch_tail_peer<R, true, true>(device, *p, pp, d_block, rank, piece, batch, st);
   switch(glog) {
     TAILPEER(1)
     TAILPEER(2)

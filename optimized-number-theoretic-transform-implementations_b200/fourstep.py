@@ -115,9 +115,10 @@ class PeerExchange:
     ordered by a flag barrier that runs as a kernel on the caller's stream (ntt_b200_peer_barrier).
     `dist` is only used once, to hand the IPC handles round."""
 
-    def __init__(self, n_local, rank, world, device, dist, group=None):
+    def __init__(self, n_local, rank, world, device, dist, group=None, batch=1):
         import ctypes as C
-        self.rank, self.world, self.device, self.n_local = rank, world, device, n_local
+        self.rank, self.world, self.device, self.n_local = rank, world, device, n_local * batch
+        n_local = n_local * batch                                  # `batch` slices one after the other
         self.slice_ptr = _pkg.device_alloc(device, n_local * 8)
         self.flags_ptr = _pkg.device_alloc(device, 512)            # `world` uint32 flags, timeout word at +256
         _pkg.memcpy_h2d(device, self.flags_ptr, np.zeros(64, dtype=np.uint64))
@@ -177,22 +178,24 @@ class FusedDistributedNtt(DistributedNtt):
     Calls must alternate forward / inverse (each barrier then also fences the previous step's peer accesses);
     to repeat the same direction, call self.px.barrier() in between."""
 
-    def __init__(self, N, q, psi, rank, world, device, dist, group=None):
+    def __init__(self, N, q, psi, rank, world, device, dist, group=None, batch=1):
+        """batch > 1: `batch` transforms share every launch and every barrier (slice buffer = batch slices of N/G
+        words one after the other, block buffer = batch blocks): one N = 2^22 exchange is latency-bound."""
         super().__init__(N, q, psi, rank, world, device)
         assert world > 1
-        self.device = device
-        self.px = PeerExchange(self.n_local, rank, world, device, dist, group)
+        self.device, self.batch = device, batch
+        self.px = PeerExchange(self.n_local, rank, world, device, dist, group, batch)
 
     def forward(self, block_dev, stream=None):
-        self.local.fwd(self.px.slice_ptr, 1, stream)
+        self.local.fwd(self.px.slice_ptr, self.batch, stream)
         self.px.barrier(stream)
-        self.full.fwd_tail_gather(self.px.slices, block_dev, self.g, self.rank, stream)
+        self.full.fwd_tail_gather(self.px.slices, block_dev, self.g, self.rank, stream, self.batch)
         return block_dev
 
     def inverse(self, block_dev, stream=None):
-        self.full.inv_tail_scatter(self.px.slices, block_dev, self.g, self.rank, stream)
+        self.full.inv_tail_scatter(self.px.slices, block_dev, self.g, self.rank, stream, self.batch)
         self.px.barrier(stream)
-        self.local.inv(self.px.slice_ptr, 1, stream)
+        self.local.inv(self.px.slice_ptr, self.batch, stream)
 
     def check(self):
         """Synchronise and raise if any peer barrier gave up waiting (k_peer_barrier reports a timeout instead of

@@ -405,24 +405,36 @@ int ntt_b200_inv_tail_block(const ntt_b200_plan_t *plan, uint64_t *d_block, uint
   return NTT_B200_SUCCESS;
 }
 
-int ntt_b200_fwd_tail_gather(const ntt_b200_plan_t *plan, uint64_t *const *peer_slices, uint64_t *d_block,
-                             uint32_t log2_parts, uint32_t rank, void *stream)
+int ntt_b200_fwd_tail_gather_batch(const ntt_b200_plan_t *plan, uint64_t *const *peer_slices, uint64_t *d_block,
+                                   uint32_t log2_parts, uint32_t rank, size_t batch, void *stream)
 {
   if(check_batch(plan, d_block, 0)) return NTT_B200_ERROR;
   if(!peer_slices) return set_error("peer slice table is NULL%s", NULL);
-  if(ntt_cuda_tail_peer(plan->device, &plan->params, peer_slices, d_block, log2_parts, rank, 0, stream))
+  if(ntt_cuda_tail_peer(plan->device, &plan->params, peer_slices, d_block, log2_parts, rank, batch, 0, stream))
     return cuda_error("forward tail (peer gather)");
   return NTT_B200_SUCCESS;
+}
+
+int ntt_b200_inv_tail_scatter_batch(const ntt_b200_plan_t *plan, uint64_t *const *peer_slices, uint64_t *d_block,
+                                    uint32_t log2_parts, uint32_t rank, size_t batch, void *stream)
+{
+  if(check_batch(plan, d_block, 1)) return NTT_B200_ERROR;
+  if(!peer_slices) return set_error("peer slice table is NULL%s", NULL);
+  if(ntt_cuda_tail_peer(plan->device, &plan->params, peer_slices, d_block, log2_parts, rank, batch, 1, stream))
+    return cuda_error("inverse tail (peer scatter)");
+  return NTT_B200_SUCCESS;
+}
+
+int ntt_b200_fwd_tail_gather(const ntt_b200_plan_t *plan, uint64_t *const *peer_slices, uint64_t *d_block,
+                             uint32_t log2_parts, uint32_t rank, void *stream)
+{
+  return ntt_b200_fwd_tail_gather_batch(plan, peer_slices, d_block, log2_parts, rank, 1, stream);
 }
 
 int ntt_b200_inv_tail_scatter(const ntt_b200_plan_t *plan, uint64_t *const *peer_slices, uint64_t *d_block,
                               uint32_t log2_parts, uint32_t rank, void *stream)
 {
-  if(check_batch(plan, d_block, 1)) return NTT_B200_ERROR;
-  if(!peer_slices) return set_error("peer slice table is NULL%s", NULL);
-  if(ntt_cuda_tail_peer(plan->device, &plan->params, peer_slices, d_block, log2_parts, rank, 1, stream))
-    return cuda_error("inverse tail (peer scatter)");
-  return NTT_B200_SUCCESS;
+  return ntt_b200_inv_tail_scatter_batch(plan, peer_slices, d_block, log2_parts, rank, 1, stream);
 }
 
 int ntt_b200_peer_barrier(int device, void *const *peer_flags, void *my_flags, uint32_t rank, uint32_t world,
