@@ -48,7 +48,8 @@ const char *ntt_b200_version(void);
  * Kernel selection, for benchmarks and A/B parity tests only (every choice is a CUDA path):
  *   "ring" 0/1  persistent TMA ring kernel for chunks of 2^12..2^14 (default 1; 0 = generic smem kernel)
  *   "fp64" 0/1  run the ring kernel's butterflies on the FP64 pipe when q <= 2^50-2048 (default 1)
- * The same switches are read from NTT_B200_NO_RING=1 / NTT_B200_NO_FP64=1 at first use.
+ *   "polymul" 0/1  one-kernel negacyclic multiply at N = 2^13 (default 1; 0 = compose it from transforms)
+ * The same switches are read from NTT_B200_NO_RING=1 / NTT_B200_NO_FP64=1 / NTT_B200_NO_FUSED_POLYMUL=1 at first use.
  */
 int ntt_b200_configure(const char *key, int value);
 
@@ -140,8 +141,11 @@ int ntt_b200_inv_rns(ntt_b200_plan_t *const *plans, size_t limbs, uint64_t *d_a,
 
 /*
  * Negacyclic product c = a * b in Z_q[X]/(X^N+1) for `batch` pairs (next row of the scope table:
- * fwd x2, pointwise multiply, inverse).  d_c may alias d_a or d_b.  d_a and d_b are overwritten (work space).
- * On the FP64 ring kernel the pointwise product is fused into the second forward transform.
+ * fwd x2, pointwise multiply, inverse).  d_c may alias d_a or d_b; d_a == d_b squares.  d_a and d_b may be
+ * overwritten (work space).  At N = 2^13 with q <= 2^50-2048 the whole product is ONE kernel: both operands sit in
+ * shared memory, both forward transforms, the product and the inverse run on chip, a and b are read once and c is
+ * written once (csrc/ntt_polymul_fp.cuh).  Other sizes compose it from transforms (on the FP64 ring kernel the
+ * pointwise product is fused into the second forward transform).
  */
 int ntt_b200_negacyclic_mul_batch(const ntt_b200_plan_t *plan, uint64_t *d_c, uint64_t *d_a, uint64_t *d_b,
                                   size_t batch, void *stream);

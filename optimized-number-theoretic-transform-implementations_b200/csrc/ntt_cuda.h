@@ -120,6 +120,9 @@ int ntt_cuda_forward_ex(int device, const ntt_cuda_params_t *p, uint64_t *d_a, s
 /* forward transform of d_a followed by d_a .*= d_other; *fused_out says whether the kernel did the product */
 int ntt_cuda_forward_mul(int device, const ntt_cuda_params_t *p, uint64_t *d_a, const uint64_t *d_other, size_t batch,
                          void *stream, int *fused_out);
+/* whole negacyclic products in one kernel where served (N = 2^13, FP64 range); *done = 0: compose from transforms */
+int ntt_cuda_polymul(int device, const ntt_cuda_params_t *p, uint64_t *d_c, uint64_t *d_a, uint64_t *d_b, size_t batch,
+                     void *stream, int *done);
 /* last `glog` stages on contiguous block `block` of a transform spread over 2^glog devices (see ntt_kernels.cu) */
 int ntt_cuda_tail(int device, const ntt_cuda_params_t *p, uint64_t *d_block, uint32_t glog, uint32_t block, int inverse,
                   void *stream);

@@ -671,7 +671,7 @@ int nl_make_block_tmap(CUtensorMap *tm, uint64_t *d_a, size_t total_words, unsig
 }  // namespace nttb200
 
 /* kernel-selection switches (benchmarks and A/B parity tests): environment at first use, or ntt_cuda_configure */
-static int g_ring_on = -1, g_fp64_on = -1;
+static int g_ring_on = -1, g_fp64_on = -1, g_polymul_on = -1;
 static bool ring_enabled()
 {
   if(g_ring_on < 0) {
@@ -684,6 +684,7 @@ extern "C" int ntt_cuda_configure(const char *key, int value)
 {
   if(key && !strcmp(key, "ring")) { g_ring_on = value ? 1 : 0; return 0; }
   if(key && !strcmp(key, "fp64")) { g_fp64_on = value ? 1 : 0; return 0; }
+  if(key && !strcmp(key, "polymul")) { g_polymul_on = value ? 1 : 0; return 0; }
   return fail_msg("unknown configuration key");
 }
 
@@ -989,6 +990,28 @@ extern "C" int ntt_cuda_forward_mul(int device, const ntt_cuda_params_t *p, uint
   memset(&o, 0, sizeof(o));
   o.d_other = d_other;
   return ntt_cuda_forward_ex(device, p, d_a, batch, stream, &o, fused_out);
+}
+
+/* c = a * b in Z_q[X]/(X^N+1), `batch` products, in ONE kernel (both operands in shared memory, nothing of the NTT
+ * domain in global memory).  *done = 0 if this plan / these pointers are not served (N != 2^13, modulus outside the
+ * FP64 range, ring kernels switched off, a or b not 128-byte aligned): the caller then composes the product from
+ * transforms.  c may alias a or b; a == b squares. */
+extern "C" int ntt_cuda_polymul(int device, const ntt_cuda_params_t *p, uint64_t *d_c, uint64_t *d_a, uint64_t *d_b,
+                                size_t batch, void *stream, int *done)
+{
+  *done = 0;
+  if(batch == 0) return 0;
+  if(p->logn != 13 || !ring_enabled() || !p->lazy || !use_fp64(*p, true) || !use_fp64(*p, false)) return 0;
+  if((((uintptr_t)d_a | (uintptr_t)d_b) & 127) != 0 || ((uintptr_t)d_c & 15) != 0) return 0;
+  if(g_polymul_on < 0) {
+    const char *e = getenv("NTT_B200_NO_FUSED_POLYMUL");
+    g_polymul_on  = (e && e[0] == '1') ? 0 : 1;
+  }
+  if(!g_polymul_on) return 0;
+  DevGuard g(device);
+  if(!g.ok) return fail_msg("cudaSetDevice failed");
+  *done = 1;
+  return polymul_fp_launch(device, *p, d_a, d_b, d_c, batch, (cudaStream_t)stream);
 }
 
 extern "C" int ntt_cuda_inverse(int device, const ntt_cuda_params_t *p, uint64_t *d_a, size_t batch, void *stream)

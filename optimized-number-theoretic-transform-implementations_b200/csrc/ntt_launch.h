@@ -39,6 +39,9 @@ int ring_fp_launch_13(bool fwd, int device, const ntt_cuda_params_t &p, uint64_t
                       const RingOpts &o);
 int ring_fp_launch_14(bool fwd, int device, const ntt_cuda_params_t &p, uint64_t *d_a, size_t n_chunks, cudaStream_t st,
                       const RingOpts &o);
+/* one-kernel negacyclic multiply, N = 2^13 (ntt_polymul_fp.cuh) */
+int polymul_fp_launch(int device, const ntt_cuda_params_t &p, uint64_t *d_a, uint64_t *d_b, uint64_t *d_c,
+                      size_t n_pairs, cudaStream_t st);
 int ring_int_launch(int L, bool fwd, int device, const ntt_cuda_params_t &p, uint64_t *d_a, size_t n_chunks,
                     cudaStream_t st);
 

@@ -562,6 +562,13 @@ int ntt_b200_negacyclic_mul_batch(const ntt_b200_plan_t *plan, uint64_t *d_c, ui
                                   size_t batch, void *stream)
 {
   if(check_batch(plan, d_a, 1) || check_batch(plan, d_b, 0) || check_batch(plan, d_c, 0)) return NTT_B200_ERROR;
+  {
+    /* N = 2^13 in the FP64 range: one kernel, both operands in shared memory (csrc/ntt_polymul_fp.cuh) */
+    int done = 0;
+    if(ntt_cuda_polymul(plan->device, &plan->params, d_c, d_a, d_b, batch, stream, &done))
+      return cuda_error("negacyclic multiply");
+    if(done) return NTT_B200_SUCCESS;
+  }
   if(d_a == d_b) {
     /* squaring: one forward transform, the NTT-domain square, the inverse (the fused second forward would read
      * its own half-transformed buffer as the other operand) */

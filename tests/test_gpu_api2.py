@@ -243,3 +243,43 @@ def test_unordered_contract(ntt, oracle, m):
     want = oracle.inv_batch(oracle.pointwise_mul(want_a, fb, q).reshape(batch, N), q, t.n_inv, t.w_inv, t.w_inv_con)
     assert np.array_equal(_host(da), want)
     plan.close()
+
+
+@pytest.mark.parametrize("bits,batch", [(49, 1), (49, 37), (50, 5), (49, 300)])
+def test_one_kernel_polymul(ntt, oracle, bits, batch):
+    """ntt_b200_negacyclic_mul_batch at N = 2^13 runs as ONE kernel (csrc/ntt_polymul_fp.cuh): every product equals
+    the oracle pipeline (forward x2, pointwise product, inverse), the composed path gives identical bytes, and the
+    aliasing forms (c = a, c = b, a = b) work.  batch 300 > 148 CTAs: several pairs per CTA through the slot ring."""
+    m, N = 13, 1 << 13
+    q = Q49 if bits == 49 else _q50(oracle, N)
+    N, psi, t = _setup(oracle, m, q)
+    a = oracle.uniform(batch * N, 4 * q, 71).reshape(batch, N)      # forward contract [0,4q)
+    b = oracle.uniform(batch * N, 4 * q, 72).reshape(batch, N)
+    a[0, :] = 4 * q - 1
+    b[0, :] = 4 * q - 1
+    fa, fb = oracle.fwd_batch(a, q, t.w, t.w_con), oracle.fwd_batch(b, q, t.w, t.w_con)
+    want = oracle.inv_batch(oracle.pointwise_mul(fa, fb, q).reshape(batch, N), q, t.n_inv, t.w_inv, t.w_inv_con)
+    want_sq = oracle.inv_batch(oracle.pointwise_mul(fa, fa, q).reshape(batch, N), q, t.n_inv, t.w_inv, t.w_inv_con)
+    plan = ntt.Plan.from_psi(N, q, psi)
+    da, db, dc = _dev(a), _dev(b), _dev(np.zeros_like(a))
+    plan.negacyclic_mul(dc, da, db, batch)
+    assert np.array_equal(_host(dc), want), "one-kernel product differs from the oracle pipeline"
+    assert np.array_equal(_host(da), a) and np.array_equal(_host(db), b), "the fused kernel leaves its operands alone"
+    da2 = _dev(a)
+    plan.negacyclic_mul(da2, da2, db, batch)                      # c aliases a
+    assert np.array_equal(_host(da2), want)
+    db2 = _dev(b)
+    plan.negacyclic_mul(db2, da, db2, batch)                      # c aliases b
+    assert np.array_equal(_host(db2), want)
+    plan.negacyclic_mul(dc, da, da, batch)                        # squaring
+    assert np.array_equal(_host(dc), want_sq)
+    try:                                                          # the composed path: identical bytes
+        ntt.configure("polymul", 0)
+        da3, db3, dc3 = _dev(a % np.uint64(q)), _dev(b % np.uint64(q)), _dev(np.zeros_like(a))
+        plan.negacyclic_mul(dc3, da3, db3, batch)
+        assert np.array_equal(_host(dc3), want)
+    finally:
+        ntt.configure("polymul", 1)
+    if batch == 1:                                                # schoolbook cross-check, independent of any NTT
+        assert np.array_equal(want[0], oracle.negacyclic_mul(a[0] % np.uint64(q), b[0] % np.uint64(q), q))
+    plan.close()
