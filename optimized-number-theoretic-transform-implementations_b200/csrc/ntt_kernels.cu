@@ -336,6 +336,40 @@ __global__ void __launch_bounds__(256) k_strided(const __grid_constant__ ntt_cud
   }
 }
 
+/* The same pass over the polynomials of SEVERAL plans in one launch (RNS limbs, lazy path): polynomial `poly` of
+ * the array belongs to plan poly / polys_per_limb, whose parameters come from the argument table. */
+template <int R, bool FWD, int OUT>
+__global__ void __launch_bounds__(256) k_strided_multi(const __grid_constant__ RingLimbs<true> limbs,
+                                                       uint64_t *__restrict__ a, uint32_t s0, size_t n_groups)
+{
+  constexpr int  n      = 1 << R;
+  const uint32_t logn   = limbs.e[0].logn;
+  const uint32_t es_log = logn - s0 - R;
+  const uint32_t gl     = logn - R;
+  for(size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_groups; t += (size_t)gridDim.x * blockDim.x) {
+    const size_t             poly = t >> gl;
+    const ntt_cuda_params_t &p    = limbs.e[(uint32_t)poly / limbs.polys_per_limb];
+    const uint32_t           g    = (uint32_t)(t & ((1u << gl) - 1u));
+    const uint32_t           i    = g >> es_log;
+    const uint32_t           j    = g & ((1u << es_log) - 1u);
+    uint64_t *               base = a + (poly << logn) + ((size_t)i << (logn - s0)) + j;
+    uint64_t                 x[n];
+#pragma unroll
+    for(int k = 0; k < n; k++) x[k] = base[(size_t)k << es_log];
+    radix_network<R, FWD, false>(x, p, s0, i);
+#pragma unroll
+    for(int k = 0; k < n; k++) {
+      uint64_t v = x[k];
+      if(OUT == 1) v = finish<false>(v, p);
+      if(OUT == 2) {
+        const Red rc{p.q, p.negq, p.red_shift, p.red_mu};
+        v = reduce_2q(v, rc);
+      }
+      base[(size_t)k << es_log] = v;
+    }
+  }
+}
+
 /* ------------------------------------------------------------------------------------------------ */
 /* table generation                                                                                  */
 /* ------------------------------------------------------------------------------------------------ */
@@ -804,6 +838,32 @@ static int dispatch_strided(int device, int R, const ntt_cuda_params_t &p, uint6
   return dispatch_strided_groups<FWD, EXACT, OUT>(device, R, p, d_a, s0, 0, batch << (p.logn - R), st);
 }
 
+template <int R, bool FWD, int OUT>
+static int launch_strided_multi(int device, const RingLimbs<true> &lb, uint64_t *d_a, uint32_t s0, size_t total_polys,
+                                cudaStream_t st)
+{
+  const size_t n_groups = total_polys << (lb.e[0].logn - R);
+  size_t       grid     = (n_groups + 255) / 256;
+  const size_t cap      = (size_t)sm_count(device) * 32;
+  if(grid > cap) grid = cap;
+  k_strided_multi<R, FWD, OUT><<<(unsigned)grid, 256, 0, st>>>(lb, d_a, s0, n_groups);
+  CU(cudaGetLastError());
+  return 0;
+}
+template <bool FWD, int OUT>
+static int dispatch_strided_multi(int device, int R, const RingLimbs<true> &lb, uint64_t *d_a, uint32_t s0,
+                                  size_t total_polys, cudaStream_t st)
+{
+  switch(R) {
+    case 1: return launch_strided_multi<1, FWD, OUT>(device, lb, d_a, s0, total_polys, st);
+    case 2: return launch_strided_multi<2, FWD, OUT>(device, lb, d_a, s0, total_polys, st);
+    case 3: return launch_strided_multi<3, FWD, OUT>(device, lb, d_a, s0, total_polys, st);
+    case 4: return launch_strided_multi<4, FWD, OUT>(device, lb, d_a, s0, total_polys, st);
+    case 5: return launch_strided_multi<5, FWD, OUT>(device, lb, d_a, s0, total_polys, st);
+    default: return fail_msg("unsupported strided radix");
+  }
+}
+
 /* How the stages of a 2^logn transform are split: `ns` strided passes of radix 2^r[i] cover the first
  * S1 = sum r[i] stages, the chunk kernel covers the remaining L = logn - S1 (<= 14). */
 struct Split {
@@ -877,9 +937,11 @@ extern "C" int ntt_cuda_plan_inverse_bounds(ntt_cuda_params_t *p)
 
 /* d_other != nullptr: also multiply pointwise by d_other (fused into the chunk kernel); *fused tells the caller
  * whether that happened (it does on the FP64 ring kernel), otherwise nothing was multiplied. */
+/* phases (RNS batches issue all strided passes before any chunk kernel): bit 0 = strided passes, bit 1 = chunk kernel */
+enum { PH_STRIDED = 1, PH_CHUNK = 2, PH_ALL = 3 };
 template <bool EXACT>
 static int forward_impl(int device, const ntt_cuda_params_t &p, uint64_t *d_a, size_t batch, cudaStream_t st,
-                        const ntt_cuda_fwd_opts_t *opts = nullptr, bool *fused = nullptr)
+                        const ntt_cuda_fwd_opts_t *opts = nullptr, bool *fused = nullptr, int phases = PH_ALL)
 {
   if(fused) *fused = false;
   const Split sp = make_split((int)p.logn);
@@ -887,11 +949,14 @@ static int forward_impl(int device, const ntt_cuda_params_t &p, uint64_t *d_a, s
   /* the FP64 chunk kernel wants inputs below 2^52: the last strided pass then hands over values below 2q */
   const bool fp_next = !EXACT && ring_enabled() && p.lazy && sp.L >= 12 && use_fp64(p, true) && ((uintptr_t)d_a & 127) == 0;
   for(int k = 0; k < sp.ns; k++) {
-    const int rc = (fp_next && k == sp.ns - 1) ? dispatch_strided<true, EXACT, 2>(device, sp.r[k], p, d_a, s0, batch, st)
-                                               : dispatch_strided<true, EXACT, 0>(device, sp.r[k], p, d_a, s0, batch, st);
-    if(rc) return -1;
+    if(phases & PH_STRIDED) {
+      const int rc = (fp_next && k == sp.ns - 1) ? dispatch_strided<true, EXACT, 2>(device, sp.r[k], p, d_a, s0, batch, st)
+                                                 : dispatch_strided<true, EXACT, 0>(device, sp.r[k], p, d_a, s0, batch, st);
+      if(rc) return -1;
+    }
     s0 += sp.r[k];
   }
+  if(!(phases & PH_CHUNK)) return 0;
   if(!EXACT) {
     bool done = false;
     if(opts && (opts->d_other || opts->lazy_out)) {
@@ -912,14 +977,18 @@ static int forward_impl(int device, const ntt_cuda_params_t &p, uint64_t *d_a, s
 }
 
 template <bool EXACT>
-static int inverse_impl(int device, const ntt_cuda_params_t &p, uint64_t *d_a, size_t batch, cudaStream_t st)
+static int inverse_impl(int device, const ntt_cuda_params_t &p, uint64_t *d_a, size_t batch, cudaStream_t st,
+                        int phases = PH_ALL)
 {
   const Split sp = make_split((int)p.logn);
   uint32_t    s1 = 0;
   for(int k = 0; k < sp.ns; k++) s1 += sp.r[k];
-  bool done = false;
-  if(!EXACT && try_ring<false>(device, sp.L, p, d_a, batch << s1, st, &done)) return -1;
-  if(!done && dispatch_chunk<false, EXACT>(device, sp.L, p, d_a, batch << s1, st)) return -1;
+  if(phases & PH_CHUNK) {
+    bool done = false;
+    if(!EXACT && try_ring<false>(device, sp.L, p, d_a, batch << s1, st, &done)) return -1;
+    if(!done && dispatch_chunk<false, EXACT>(device, sp.L, p, d_a, batch << s1, st)) return -1;
+  }
+  if(!(phases & PH_STRIDED)) return 0;
   uint32_t s0 = s1;
   for(int k = sp.ns - 1; k >= 0; k--) {
     s0 -= sp.r[k];
@@ -1275,12 +1344,68 @@ extern "C" int ntt_cuda_ipc_close(int device, void *d_ptr)
  * and a ragged tail, so the limbs are issued round-robin on a few internal streams, each launch sized to a
  * fraction of the GPU (see g_min_chunks_per_cta); `stream` forks into them and joins again.
  */
+/* All limbs in ONE launch per kernel (strided pass(es) + FP64 chunk kernel over the whole limb-major array): what an
+ * RNS batch of N >= 2^14 in the FP64 range gets.  A launch per limb gives every persistent CTA three or four chunks
+ * and leaves SMs idle between limbs; one launch gives it dozens (config 3: 0.99 -> see profiles). */
+static int rns_multi_launch(int device, const ntt_cuda_params_t *const *plist, size_t limbs, uint64_t *d_a,
+                            size_t batch_per_limb, int inverse, cudaStream_t st)
+{
+  const ntt_cuda_params_t &p0 = *plist[0];
+  const Split              sp = make_split((int)p0.logn);
+  static thread_local RingLimbs<true> lb;
+  for(size_t l = 0; l < limbs; l++) lb.e[l] = *plist[l];
+  lb.polys_per_limb = (uint32_t)batch_per_limb;
+  const size_t total = limbs * batch_per_limb;
+  uint32_t     s1    = 0;
+  for(int k = 0; k < sp.ns; k++) s1 += sp.r[k];
+  if(!inverse) {
+    uint32_t s0 = 0;
+    for(int k = 0; k < sp.ns; k++) {
+      const int rc = (k == sp.ns - 1) ? dispatch_strided_multi<true, 2>(device, sp.r[k], lb, d_a, s0, total, st)
+                                      : dispatch_strided_multi<true, 0>(device, sp.r[k], lb, d_a, s0, total, st);
+      if(rc) return -1;
+      s0 += sp.r[k];
+    }
+    return ring_fp_launch_multi_14(true, device, plist, limbs, batch_per_limb, d_a, st);
+  }
+  if(ring_fp_launch_multi_14(false, device, plist, limbs, batch_per_limb, d_a, st)) return -1;
+  uint32_t s0 = s1;
+  for(int k = sp.ns - 1; k >= 0; k--) {
+    s0 -= sp.r[k];
+    const int rc = (k == 0) ? dispatch_strided_multi<false, 1>(device, sp.r[k], lb, d_a, s0, total, st)
+                            : dispatch_strided_multi<false, 0>(device, sp.r[k], lb, d_a, s0, total, st);
+    if(rc) return -1;
+  }
+  return 0;
+}
+
+static bool rns_multi_ok(const ntt_cuda_params_t *const *plist, size_t limbs, const uint64_t *d_a, size_t batch_per_limb,
+                         int inverse)
+{
+  static int on = -1;
+  if(on < 0) {
+    const char *e = getenv("NTT_B200_NO_RNS_MULTI");
+    on            = (e && e[0] == '1') ? 0 : 1;
+  }
+  if(!on || limbs < 2 || limbs > (size_t)RING_MAX_LIMBS || !ring_enabled()) return false;
+  if(((uintptr_t)d_a & 127) != 0 || batch_per_limb >= ((size_t)1 << 31)) return false;
+  const ntt_cuda_params_t &p0 = *plist[0];
+  if(p0.logn < 14 || ((limbs * batch_per_limb) << (p0.logn - 14)) >= ((size_t)1 << 31)) return false;
+  for(size_t l = 0; l < limbs; l++) {
+    const ntt_cuda_params_t &p = *plist[l];
+    if(p.logn != p0.logn || !p.lazy || p.fp64 != p0.fp64 || !use_fp64(p, !inverse)) return false;
+  }
+  return true;
+}
+
 extern "C" int ntt_cuda_rns(int device, const ntt_cuda_params_t *const *plist, size_t limbs, uint64_t *d_a,
                             size_t batch_per_limb, int inverse, void *stream)
 {
   if(limbs == 0 || batch_per_limb == 0) return 0;
   DevGuard g(device);
   if(!g.ok) return fail_msg("cudaSetDevice failed");
+  if(rns_multi_ok(plist, limbs, d_a, batch_per_limb, inverse))
+    return rns_multi_launch(device, plist, limbs, d_a, batch_per_limb, inverse, (cudaStream_t)stream);
   constexpr int       NS = 4;
   static cudaStream_t side[64][NS];
   static cudaEvent_t  fork_ev[64], join_ev[64][NS];
@@ -1304,15 +1429,27 @@ extern "C" int ntt_cuda_rns(int device, const ntt_cuda_params_t *const *plist, s
   CU(cudaEventRecord(fork_ev[dv], user));
   for(int i = 0; i < lanes; i++) CU(cudaStreamWaitEvent(side[dv][i], fork_ev[dv], 0));
   int rc = 0;
-  g_min_chunks_per_cta = 4;
-  for(size_t l = 0; l < limbs && !rc; l++) {
-    const ntt_cuda_params_t &p  = *plist[l];
-    cudaStream_t             st = side[dv][l % lanes];
-    uint64_t *               d  = d_a + l * limb_words;
-    if(inverse) {
-      rc = p.lazy ? inverse_impl<false>(device, p, d, batch_per_limb, st) : inverse_impl<true>(device, p, d, batch_per_limb, st);
-    } else {
-      rc = p.lazy ? forward_impl<false>(device, p, d, batch_per_limb, st) : forward_impl<true>(device, p, d, batch_per_limb, st);
+  /* N >= 2^15: every limb is a strided pass plus a chunk kernel.  Issued limb by limb the small strided grids of one
+   * limb queue behind the SM-filling chunk kernels of the others; issued phase by phase (all strided passes of a
+   * stream first, then its chunk kernels -- the per-limb order on a stream is unchanged) the two kinds of kernel do
+   * not interleave.  Chunk kernels of `lanes` limbs run side by side, each on its share of the SMs. */
+  size_t share = ((size_t)sm_count(device) + lanes - 1) / lanes;
+  const size_t chunks_per_limb = batch_per_limb << (plist[0]->logn > 14 ? plist[0]->logn - 14 : 0);
+  g_min_chunks_per_cta = (chunks_per_limb + share - 1) / share;
+  if(g_min_chunks_per_cta < 1) g_min_chunks_per_cta = 1;
+  const int first_phase = inverse ? PH_CHUNK : PH_STRIDED, second_phase = inverse ? PH_STRIDED : PH_CHUNK;
+  for(int phase = 0; phase < 2 && !rc; phase++) {
+    const int ph = phase == 0 ? first_phase : second_phase;
+    for(size_t l = 0; l < limbs && !rc; l++) {
+      const ntt_cuda_params_t &p  = *plist[l];
+      cudaStream_t             st = side[dv][l % lanes];
+      uint64_t *               d  = d_a + l * limb_words;
+      if(inverse) {
+        rc = p.lazy ? inverse_impl<false>(device, p, d, batch_per_limb, st, ph) : inverse_impl<true>(device, p, d, batch_per_limb, st, ph);
+      } else {
+        rc = p.lazy ? forward_impl<false>(device, p, d, batch_per_limb, st, nullptr, nullptr, ph)
+                    : forward_impl<true>(device, p, d, batch_per_limb, st, nullptr, nullptr, ph);
+      }
     }
   }
   g_min_chunks_per_cta = 0;

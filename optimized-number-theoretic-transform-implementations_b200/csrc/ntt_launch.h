@@ -24,6 +24,19 @@ int nl_make_block_tmap(CUtensorMap *tm, uint64_t *d_a, size_t total_words, unsig
 /* several small launches side by side (RNS limbs): chunks every CTA should at least get; 0 = use the whole GPU */
 size_t nl_min_chunks_per_cta();
 
+/* Parameters of several plans for ONE launch (RNS limbs: same N, one modulus and one set of tables each; limb l
+ * owns polys_per_limb consecutive polynomials of the array).  Travels as a kernel argument (constant bank). */
+constexpr int RING_MAX_LIMBS = 48;
+template <bool MULTI>
+struct RingLimbs {
+  ntt_cuda_params_t e[MULTI ? RING_MAX_LIMBS : 1];
+  uint32_t          polys_per_limb;
+};
+template <>
+struct RingLimbs<false> {
+  uint32_t polys_per_limb;
+};
+
 /* what the forward ring kernel may be asked to do on top of the transform */
 struct RingOpts {
   const uint64_t *d_other    = nullptr; /* multiply pointwise by this transform-domain array before storing */
@@ -42,6 +55,9 @@ int ring_fp_launch_14(bool fwd, int device, const ntt_cuda_params_t &p, uint64_t
 /* one-kernel negacyclic multiply, N = 2^13 (ntt_polymul_fp.cuh) */
 int polymul_fp_launch(int device, const ntt_cuda_params_t &p, uint64_t *d_a, uint64_t *d_b, uint64_t *d_c,
                       size_t n_pairs, cudaStream_t st);
+/* one launch of the L = 14 FP64 ring kernel over the chunks of several plans (same N, same range schedule) */
+int ring_fp_launch_multi_14(bool fwd, int device, const ntt_cuda_params_t *const *plist, size_t n_limbs,
+                            size_t polys_per_limb, uint64_t *d_a, cudaStream_t st);
 int ring_int_launch(int L, bool fwd, int device, const ntt_cuda_params_t &p, uint64_t *d_a, size_t n_chunks,
                     cudaStream_t st);
 

@@ -251,13 +251,29 @@ __device__ long long g_trace[16 * 64 * 8]; /* [warp][poly][event] for CTA 0 */
  *              the last fold is kept (the values must fit the window) but the sign correction is not.
  * p_out: the array itself (the inverse writes its results directly). */
 enum { RING_PLAIN = 0, RING_MUL = 1, RING_LAZY = 2 };
-template <int L, bool FWD, int MODE = RING_PLAIN, bool Q50 = false>
+/*
+ * MULTI: one launch over the chunks of SEVERAL plans (RNS limbs: same N, one modulus and one set of tables each;
+ * limb l owns polys_per_limb consecutive polynomials of the array).  The per-limb parameters travel as a kernel
+ * argument (constant bank, indexed by the limb of the chunk at hand); a CTA works on a CONTIGUOUS range of the
+ * chunk sequence ordered (chunk-in-polynomial, limb, polynomial), so that the limb -- and with it the twiddle
+ * cache -- changes a couple of times per CTA at most.  One launch gives every CTA dozens of chunks to pipeline
+ * where a launch per limb gives it three or four.
+ */
+template <bool MULTI>
+__device__ __forceinline__ const ntt_cuda_params_t &ring_plan_of(const ntt_cuda_params_t &p0, const RingLimbs<MULTI> &limbs,
+                                                                  uint32_t limb)
+{
+  if constexpr(MULTI) return limbs.e[limb];
+  else return p0;
+}
+template <int L, bool FWD, int MODE = RING_PLAIN, bool Q50 = false, bool MULTI = false>
 __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
-  k_ring_fp(const __grid_constant__ ntt_cuda_params_t p, const __grid_constant__ CUtensorMap tmap,
+  k_ring_fp(const __grid_constant__ ntt_cuda_params_t p0, const __grid_constant__ CUtensorMap tmap,
             const __grid_constant__ CUtensorMap tmap2, size_t n_chunks, uint64_t *__restrict__ p_out,
-            const uint64_t *__restrict__ p_other, size_t other_mask)
+            const uint64_t *__restrict__ p_other, size_t other_mask, const __grid_constant__ RingLimbs<MULTI> limbs)
 {
   constexpr bool MUL = MODE == RING_MUL, LAZY = MODE == RING_LAZY;
+  static_assert(!MULTI || MODE == RING_PLAIN, "the multi-plan launch serves plain transforms");
   static_assert(FWD || MODE == RING_PLAIN, "the fused product and the lazy output belong to the forward kernel");
   using C = RingCfg<L>;
   constexpr int NB = C::NB, RA = C::RA, SLOTS = C::SLOTS, T = C::THREADS, HALF = NB / 2;
@@ -278,23 +294,35 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
   const uint32_t cta_bar  = bars + 8u * (2u * C::NBAR);
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t s1        = p.logn - L;
-  const size_t   my_polys  = (n_chunks > blockIdx.x) ? (n_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const uint32_t s1        = p0.logn - L;
+  /* which chunks this CTA works on: every gridDim-th chunk (single plan), or a contiguous range of the sequence
+   * ordered (chunk-in-polynomial, limb, polynomial) (several plans) */
+  const uint32_t n_polys_all = (uint32_t)(n_chunks >> s1);
+  const size_t   range_lo  = MULTI ? (size_t)blockIdx.x * n_chunks / gridDim.x : 0;
+  const size_t   range_hi  = MULTI ? (size_t)(blockIdx.x + 1) * n_chunks / gridDim.x : 0;
+  const size_t   my_polys  = MULTI ? range_hi - range_lo
+                                   : ((n_chunks > blockIdx.x) ? (n_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0);
+  auto chunk_of = [&](size_t k) -> size_t {
+    if(!MULTI) return blockIdx.x + k * gridDim.x;
+    const uint32_t i = (uint32_t)(range_lo + k), cpv = i / n_polys_all, rest = i - cpv * n_polys_all;
+    return ((size_t)rest << s1) + cpv;
+  };
   const size_t   my_blocks = my_polys * NB;
-  const size_t   groups    = (size_t)1 << (p.logn - 4);
-  const FpC      c{p.q_fd, p.qinv_fd, NTT_FP_MAGIC};
-  /* the conversion centres the input: forward [0,4q) -> [-2q,2q), inverse [0,2q) -> [-q,q) */
-  const double   in_bias = -(4503599627370496.0 + (FWD ? 2.0 * p.q_fd : p.q_fd));
-  const double   q_bias = NTT_FP_MAGIC + p.q_fd; /* lazy output: v + q lands in (0, 2q) */
-  const double2 *g_fd  = (const double2 *)(FWD ? p.fwd_fd : p.inv_fd);
-  const double2 *g_ct  = (const double2 *)(FWD ? p.fwd_ct_fd : p.inv_ct_fd);
+  const size_t   groups    = (size_t)1 << (p0.logn - 4);
+  /* single plan: the constants of the transform are loop invariants (kept out of the loop by hand: hoisting them
+   * from inside changed the schedule of the headline kernel by half a percent) */
+  const FpC      c0{p0.q_fd, p0.qinv_fd, NTT_FP_MAGIC};
+  const double   in_bias0 = -(4503599627370496.0 + (FWD ? 2.0 * p0.q_fd : p0.q_fd));
+  const double   q_bias0  = NTT_FP_MAGIC + p0.q_fd;
+  const double2 *g_fd0    = (const double2 *)(FWD ? p0.fwd_fd : p0.inv_fd);
+  const double2 *g_ct0    = (const double2 *)(FWD ? p0.fwd_ct_fd : p0.inv_ct_fd);
 
   auto slot_addr  = [&](size_t g) -> uint32_t { return ring + (uint32_t)(g % SLOTS) * 4096u; };
   auto issue_load = [&](size_t g) {
     if(g >= my_blocks) return;
     const size_t   k     = g / NB;
     const uint32_t b     = (uint32_t)(g % NB);
-    const size_t   chunk = blockIdx.x + k * gridDim.x;
+    const size_t   chunk = chunk_of(k);
     /* two barriers per polynomial in flight: blocks [0,HALF) and [HALF,NB).  The low half always sits in slots
      * that were free long ago; the high half may have been re-armed only when the previous polynomial was
      * stored, so the inverse starts on the low half while the rest is still landing. */
@@ -310,7 +338,7 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
     if(g >= my_blocks) return;
     const size_t   k     = g / NB;
     const uint32_t b     = (uint32_t)(g % NB);
-    const size_t   chunk = blockIdx.x + k * gridDim.x;
+    const size_t   chunk = chunk_of(k);
     const uint32_t bar = bars + 8u * (2u * (uint32_t)(k % C::NBAR) + (b >= (uint32_t)HALF ? 1u : 0u));
     mbar_arrive_expect_tx(bar, 4096u * C::BOXB);
     tma_load_block(slot_addr(g), &tmap2, (int)((chunk << (L - 4)) + b * 32u), bar);
@@ -334,9 +362,20 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
   bool     c1_done   = false; /* inverse: this warp already ran pass C on the first block of polynomial k */
   uint32_t sl_next = 0; /* slot of block 0 of the next polynomial: (k * NB) mod SLOTS, kept in 32 bits */
   for(size_t k = 0; k < my_polys; k++) {
-    const size_t   chunk = blockIdx.x + k * gridDim.x;
+    const size_t   chunk = MULTI ? chunk_of(k) : blockIdx.x + k * gridDim.x;
     const uint32_t cp    = (uint32_t)(chunk & (((size_t)1 << s1) - 1));
-    if(cp != cached_cp) {
+    uint32_t       limb  = 0;
+    if constexpr(MULTI) limb = (uint32_t)(chunk >> s1) / limbs.polys_per_limb;
+    /* the plan of this chunk: the kernel's own (single plan), or the limb's entry of the argument table */
+    const ntt_cuda_params_t &p = ring_plan_of<MULTI>(p0, limbs, limb);
+    const FpC      c = MULTI ? FpC{p.q_fd, p.qinv_fd, NTT_FP_MAGIC} : c0;
+    /* the conversion centres the input: forward [0,4q) -> [-2q,2q), inverse [0,2q) -> [-q,q) */
+    const double   in_bias = MULTI ? -(4503599627370496.0 + (FWD ? 2.0 * p.q_fd : p.q_fd)) : in_bias0;
+    const double   q_bias = MULTI ? NTT_FP_MAGIC + p.q_fd : q_bias0; /* lazy output: v + q lands in (0, 2q) */
+    const double2 *g_fd  = MULTI ? (const double2 *)(FWD ? p.fwd_fd : p.inv_fd) : g_fd0;
+    const double2 *g_ct  = MULTI ? (const double2 *)(FWD ? p.fwd_ct_fd : p.inv_ct_fd) : g_ct0;
+    const uint32_t cache_key = MULTI ? ((limb << 8) | cp) : cp;
+    if(cache_key != cached_cp) {
       __syncthreads();
       for(uint32_t e = tid; e < (uint32_t)C::NTW; e += T) {
         uint32_t t, st, blk;
@@ -352,7 +391,7 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
       if constexpr(TWC0) {
         for(uint32_t e = tid; e < (uint32_t)C::NTW_C0; e += T) tw_s[C::NTW + e] = __ldg(g_ct + (size_t)cp * NB * 32 + e);
       }
-      cached_cp = cp;
+      cached_cp = cache_key;
       __syncthreads();
     }
     const size_t   g0  = k * NB;
@@ -365,7 +404,7 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
     if(tid < (uint32_t)NB) {
       const size_t g = g0 + SLOTS + tid;
       if(g < my_blocks) {
-        const size_t ck = blockIdx.x + (g / NB) * gridDim.x;
+        const size_t ck = chunk_of(g / NB);
         tma_prefetch_block_l2(&tmap, (int)((ck << (L - 4)) + (uint32_t)(g % NB) * 32u));
       }
     }
@@ -564,9 +603,13 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
       if(PIPE_C1) {
         __syncwarp(); /* orders the other lanes' pass-B stores before lane 0's releasing arrive */
         if(lane == 0) mbar_arrive(cta_bar);
-        if(k + 1 < my_polys) {
+        bool prerun = k + 1 < my_polys;
+        if constexpr(MULTI) { /* the next chunk must belong to the same plan: pass C runs with this one's constants */
+          if(prerun) prerun = (uint32_t)(chunk_of(k + 1) >> s1) / limbs.polys_per_limb == limb;
+        }
+        if(prerun) {
           mbar_wait(bars + 16u * (uint32_t)((k + 1) % C::NBAR), (uint32_t)(((k + 1) / C::NBAR) & 1));
-          const size_t nchunk = chunk + gridDim.x;
+          const size_t nchunk = MULTI ? chunk_of(k + 1) : chunk + gridDim.x;
           pass_c_at(sl_next + warp, warp, (uint32_t)(nchunk & (((size_t)1 << s1) - 1)), nchunk, false);
           c1_done = true;
         }

@@ -15,7 +15,7 @@ static int ring_fp_launch_one(int device, const ntt_cuda_params_t &p, const CUte
     NL_CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_FP));
     ready[device & 63] = true;
   }
-  kern<<<grid, C::THREADS, C::SMEM_FP, st>>>(p, tm, tm2, n_chunks, d_a, o.d_other, o.other_mask);
+  kern<<<grid, C::THREADS, C::SMEM_FP, st>>>(p, tm, tm2, n_chunks, d_a, o.d_other, o.other_mask, RingLimbs<false>{0});
   NL_CU(cudaGetLastError());
   return 0;
 }
@@ -69,6 +69,54 @@ int NTT_RING_CAT(ring_fp_launch_, NTT_RING_L)(bool fwd, int device, const ntt_cu
 #endif
 
 }  // namespace nttb200
+
+#if NTT_RING_L == 14 && !defined(NTT_EXPERIMENT)
+namespace nttb200 {
+/* One launch over the chunks of several plans (RNS limbs), see k_ring_fp<..., MULTI>.  All plans share N and the
+ * range schedule; limb l owns polys_per_limb consecutive polynomials of d_a. */
+template <bool FWD, bool Q50>
+static int ring_fp_launch_multi_one(int device, const ntt_cuda_params_t *const *plist, size_t n_limbs,
+                                    size_t polys_per_limb, const CUtensorMap &tm, const CUtensorMap &tm2, unsigned grid,
+                                    uint64_t *d_a, size_t n_chunks, cudaStream_t st)
+{
+  using C               = RingCfg<14>;
+  auto        kern      = k_ring_fp<14, FWD, RING_PLAIN, Q50, true>;
+  static bool ready[64] = {false};
+  if(!ready[device & 63]) {
+    NL_CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_FP));
+    ready[device & 63] = true;
+  }
+  static thread_local RingLimbs<true> lb; /* 21 KiB: kept off the stack */
+  for(size_t l = 0; l < n_limbs; l++) lb.e[l] = *plist[l];
+  lb.polys_per_limb = (uint32_t)polys_per_limb;
+  kern<<<grid, C::THREADS, C::SMEM_FP, st>>>(*plist[0], tm, tm2, n_chunks, d_a, nullptr, ~(size_t)0, lb);
+  NL_CU(cudaGetLastError());
+  return 0;
+}
+
+int ring_fp_launch_multi_14(bool fwd, int device, const ntt_cuda_params_t *const *plist, size_t n_limbs,
+                            size_t polys_per_limb, uint64_t *d_a, cudaStream_t st)
+{
+  using C = RingCfg<14>;
+  if(n_limbs < 1 || n_limbs > (size_t)RING_MAX_LIMBS) return nl_fail_msg("multi-plan launch: 1..48 plans");
+  const ntt_cuda_params_t &p  = *plist[0];
+  const size_t             n_chunks = (n_limbs * polys_per_limb) << (p.logn - 14);
+  if(n_chunks >= ((size_t)1 << 31) || polys_per_limb >= ((size_t)1 << 31)) return nl_fail_msg("multi-plan launch: batch too large");
+  CUtensorMap tm, tm2;
+  if(nl_make_block_tmap(&tm, d_a, n_chunks << 14, 32)) return -1;
+  if(nl_make_block_tmap(&tm2, d_a, n_chunks << 14, 32 * C::BOXB)) return -1;
+  size_t grid = (size_t)nl_sm_count(device);
+  if(grid > n_chunks) grid = n_chunks;
+  const bool q50 = p.fp64 == 2;
+  if(fwd) {
+    return q50 ? ring_fp_launch_multi_one<true, true>(device, plist, n_limbs, polys_per_limb, tm, tm2, (unsigned)grid, d_a, n_chunks, st)
+               : ring_fp_launch_multi_one<true, false>(device, plist, n_limbs, polys_per_limb, tm, tm2, (unsigned)grid, d_a, n_chunks, st);
+  }
+  return q50 ? ring_fp_launch_multi_one<false, true>(device, plist, n_limbs, polys_per_limb, tm, tm2, (unsigned)grid, d_a, n_chunks, st)
+             : ring_fp_launch_multi_one<false, false>(device, plist, n_limbs, polys_per_limb, tm, tm2, (unsigned)grid, d_a, n_chunks, st);
+}
+}  // namespace nttb200
+#endif
 
 #if defined(NTT_RING_TRACE) && NTT_RING_L == 14
 /* -DNTT_RING_TRACE builds only: phase timestamps of CTA 0 (tools/trace_phases.py) */

@@ -283,3 +283,43 @@ def test_one_kernel_polymul(ntt, oracle, bits, batch):
     if batch == 1:                                                # schoolbook cross-check, independent of any NTT
         assert np.array_equal(want[0], oracle.negacyclic_mul(a[0] % np.uint64(q), b[0] % np.uint64(q), q))
     plan.close()
+
+
+@pytest.mark.parametrize("m,limbs,per,bits", [(16, 5, 3, 50), (14, 4, 9, 49), (15, 48, 2, 50), (17, 3, 1, 49)])
+def test_rns_single_launch_matches_oracle_and_per_limb_path(ntt, oracle, m, limbs, per, bits):
+    """RNS batches of N >= 2^14 in the FP64 range run as ONE launch per kernel over all limbs (k_ring_fp<.., MULTI>,
+    k_strided_multi): every limb equals the oracle with its own modulus, the inverse returns the input, and the
+    launch-per-limb path (NTT_B200_NO_RING... switched by configure("fp64", 0) -> integer kernels) gives the same bytes."""
+    N = 1 << m
+    top = (1 << bits) - (2048 if bits == 50 else 1024)
+    qs, q = [], (1 << bits) + 1
+    q -= (q - 1) % (2 * N)
+    while len(qs) < limbs:
+        q -= 2 * N
+        if q <= top and oracle.is_prime(q):
+            qs.append(q)
+    plans, tabs, ins = [], [], []
+    for l, ql in enumerate(qs):
+        psi = oracle.min_root(N, ql)
+        plans.append(ntt.Plan.from_psi(N, ql, psi))
+        tabs.append(CaseTables(oracle, m, ql, psi, oracle.invmod(psi, ql), oracle.invmod(N, ql)))
+        ins.append(oracle.uniform(per * N, 4 * ql, 90 + l).reshape(per, N))     # forward contract [0,4q)
+    a = np.stack(ins)
+    d = _dev(a)
+    ntt.fwd_rns(plans, d, per)
+    f = _host(d).reshape(limbs, per, N)
+    for l in range(limbs):
+        assert np.array_equal(f[l], oracle.fwd_batch(ins[l], qs[l], tabs[l].w, tabs[l].w_con)), "limb %d forward" % l
+    ntt.inv_rns(plans, d, per)
+    back = _host(d).reshape(limbs, per, N)
+    for l in range(limbs):
+        assert np.array_equal(back[l], ins[l] % np.uint64(qs[l])), "limb %d round trip" % l
+    try:                                        # the integer kernels, one launch per limb: identical bytes
+        ntt.configure("fp64", 0)
+        d2 = _dev(a)
+        ntt.fwd_rns(plans, d2, per)
+        assert np.array_equal(_host(d2).reshape(limbs, per, N), f)
+    finally:
+        ntt.configure("fp64", 1)
+    for p in plans:
+        p.close()
