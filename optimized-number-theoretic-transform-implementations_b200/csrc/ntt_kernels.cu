@@ -336,6 +336,51 @@ __global__ void __launch_bounds__(256) k_strided(const __grid_constant__ ntt_cud
   }
 }
 
+/* Two adjacent groups per thread (16-byte loads and stores; both groups sit in the same block and share their
+ * twiddles): the pass is HBM-bound and the 8-byte version reaches 4.8 TB/s (profiles/r02e_ncu_strided.txt).
+ * Needs an even group stride (es >= 2), even first_group / n_groups and 16-byte aligned data; R <= 4. */
+template <int R, bool FWD, bool EXACT, int OUT>
+__global__ void __launch_bounds__(256) k_strided_v2(const __grid_constant__ ntt_cuda_params_t p,
+                                                    uint64_t *__restrict__ a, uint32_t s0, size_t first_group,
+                                                    size_t n_groups)
+{
+  constexpr int  n      = 1 << R;
+  const uint32_t logn   = p.logn;
+  const uint32_t es_log = logn - s0 - R;
+  const uint32_t gl     = logn - R;
+  for(size_t t2 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t2 < n_groups / 2; t2 += (size_t)gridDim.x * blockDim.x) {
+    const size_t   t    = first_group + 2 * t2;
+    const size_t   poly = t >> gl;
+    const uint32_t g    = (uint32_t)(t & ((1u << gl) - 1u));
+    const uint32_t i    = g >> es_log;
+    const uint32_t j    = g & ((1u << es_log) - 1u);
+    uint64_t *     base = a + (poly << logn) + ((size_t)i << (logn - s0)) + j;
+    uint64_t       x0[n], x1[n];
+#pragma unroll
+    for(int k = 0; k < n; k++) {
+      const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(base + ((size_t)k << es_log));
+      x0[k] = v.x;
+      x1[k] = v.y;
+    }
+    radix_network<R, FWD, EXACT>(x0, p, s0, i);
+    radix_network<R, FWD, EXACT>(x1, p, s0, i);
+#pragma unroll
+    for(int k = 0; k < n; k++) {
+      ulonglong2 v = make_ulonglong2(x0[k], x1[k]);
+      if(OUT == 1) {
+        v.x = finish<EXACT>(v.x, p);
+        v.y = finish<EXACT>(v.y, p);
+      }
+      if(OUT == 2 && !EXACT) {
+        const Red rc{p.q, p.negq, p.red_shift, p.red_mu};
+        v.x = reduce_2q(v.x, rc);
+        v.y = reduce_2q(v.y, rc);
+      }
+      *reinterpret_cast<ulonglong2 *>(base + ((size_t)k << es_log)) = v;
+    }
+  }
+}
+
 /* The same pass over the polynomials of SEVERAL plans in one launch (RNS limbs, lazy path): polynomial `poly` of
  * the array belongs to plan poly / polys_per_limb, whose parameters come from the argument table. */
 template <int R, bool FWD, int OUT>
@@ -809,8 +854,25 @@ template <int R, bool FWD, bool EXACT, int OUT>
 static int launch_strided(int device, const ntt_cuda_params_t &p, uint64_t *d_a, uint32_t s0, size_t first_group,
                           size_t n_groups, cudaStream_t st)
 {
-  size_t       grid = (n_groups + 255) / 256;
-  const size_t cap  = (size_t)sm_count(device) * 32;
+  const size_t cap = (size_t)sm_count(device) * 32;
+  if constexpr(R <= 4) {
+    /* measured (profiles/r02_kernel_experiments.txt): a gain at radix 4 (N = 2^16: 0.540 -> 0.503 ms per 1024),
+     * a loss at radix 16 (registers); NTT_B200_STRIDED_V2_MAXR overrides the largest radix exponent it is used for */
+    static int v2_maxr = -1;
+    if(v2_maxr < 0) {
+      const char *e = getenv("NTT_B200_STRIDED_V2_MAXR");
+      v2_maxr       = e ? atoi(e) : 2;
+    }
+    const uint32_t es_log = p.logn - s0 - R;
+    if(R <= v2_maxr && es_log >= 1 && (first_group & 1) == 0 && (n_groups & 1) == 0 && ((uintptr_t)d_a & 15) == 0) {
+      size_t grid = (n_groups / 2 + 255) / 256;
+      if(grid > cap) grid = cap;
+      k_strided_v2<R, FWD, EXACT, OUT><<<(unsigned)grid, 256, 0, st>>>(p, d_a, s0, first_group, n_groups);
+      CU(cudaGetLastError());
+      return 0;
+    }
+  }
+  size_t grid = (n_groups + 255) / 256;
   if(grid > cap) grid = cap;
   k_strided<R, FWD, EXACT, OUT><<<(unsigned)grid, 256, 0, st>>>(p, d_a, s0, first_group, n_groups);
   CU(cudaGetLastError());
@@ -838,13 +900,65 @@ static int dispatch_strided(int device, int R, const ntt_cuda_params_t &p, uint6
   return dispatch_strided_groups<FWD, EXACT, OUT>(device, R, p, d_a, s0, 0, batch << (p.logn - R), st);
 }
 
+/* k_strided_multi with two adjacent groups per thread (see k_strided_v2) */
+template <int R, bool FWD, int OUT>
+__global__ void __launch_bounds__(256) k_strided_multi_v2(const __grid_constant__ RingLimbs<true> limbs,
+                                                          uint64_t *__restrict__ a, uint32_t s0, size_t n_groups)
+{
+  constexpr int  n      = 1 << R;
+  const uint32_t logn   = limbs.e[0].logn;
+  const uint32_t es_log = logn - s0 - R;
+  const uint32_t gl     = logn - R;
+  for(size_t t2 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t2 < n_groups / 2; t2 += (size_t)gridDim.x * blockDim.x) {
+    const size_t             t    = 2 * t2;
+    const size_t             poly = t >> gl;
+    const ntt_cuda_params_t &p    = limbs.e[(uint32_t)poly / limbs.polys_per_limb];
+    const uint32_t           g    = (uint32_t)(t & ((1u << gl) - 1u));
+    const uint32_t           i    = g >> es_log;
+    const uint32_t           j    = g & ((1u << es_log) - 1u);
+    uint64_t *               base = a + (poly << logn) + ((size_t)i << (logn - s0)) + j;
+    uint64_t                 x0[n], x1[n];
+#pragma unroll
+    for(int k = 0; k < n; k++) {
+      const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(base + ((size_t)k << es_log));
+      x0[k] = v.x;
+      x1[k] = v.y;
+    }
+    radix_network<R, FWD, false>(x0, p, s0, i);
+    radix_network<R, FWD, false>(x1, p, s0, i);
+#pragma unroll
+    for(int k = 0; k < n; k++) {
+      ulonglong2 v = make_ulonglong2(x0[k], x1[k]);
+      if(OUT == 1) {
+        v.x = finish<false>(v.x, p);
+        v.y = finish<false>(v.y, p);
+      }
+      if(OUT == 2) {
+        const Red rc{p.q, p.negq, p.red_shift, p.red_mu};
+        v.x = reduce_2q(v.x, rc);
+        v.y = reduce_2q(v.y, rc);
+      }
+      *reinterpret_cast<ulonglong2 *>(base + ((size_t)k << es_log)) = v;
+    }
+  }
+}
+
 template <int R, bool FWD, int OUT>
 static int launch_strided_multi(int device, const RingLimbs<true> &lb, uint64_t *d_a, uint32_t s0, size_t total_polys,
                                 cudaStream_t st)
 {
   const size_t n_groups = total_polys << (lb.e[0].logn - R);
-  size_t       grid     = (n_groups + 255) / 256;
   const size_t cap      = (size_t)sm_count(device) * 32;
+  if constexpr(R <= 2) {
+    if(lb.e[0].logn - s0 - R >= 1 && ((uintptr_t)d_a & 15) == 0) {
+      size_t grid = (n_groups / 2 + 255) / 256;
+      if(grid > cap) grid = cap;
+      k_strided_multi_v2<R, FWD, OUT><<<(unsigned)grid, 256, 0, st>>>(lb, d_a, s0, n_groups);
+      CU(cudaGetLastError());
+      return 0;
+    }
+  }
+  size_t grid = (n_groups + 255) / 256;
   if(grid > cap) grid = cap;
   k_strided_multi<R, FWD, OUT><<<(unsigned)grid, 256, 0, st>>>(lb, d_a, s0, n_groups);
   CU(cudaGetLastError());
