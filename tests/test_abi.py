@@ -78,3 +78,31 @@ def test_argument_validation_messages(ntt):
     assert rc == -1 and b"odd" in ntt.lib.ntt_b200_last_error()
     rc = ntt.lib.ntt_b200_plan_create_psi(ctypes.byref(h), 0, 256, 1 << 62, 62)
     assert rc == -1
+
+
+def test_shard_range_covers_the_batch_contiguously(ntt):
+    """ntt_b200_shard_range (pure host arithmetic): contiguous shards, sizes differ by at most one, every unit once."""
+    import ctypes as C
+    for batch in (0, 1, 7, 48, 4096, 4099):
+        for parts in (1, 2, 3, 8):
+            pos, sizes = 0, []
+            for i in range(parts):
+                f, c = C.c_size_t(), C.c_size_t()
+                ntt.lib.ntt_b200_shard_range(batch, parts, i, C.byref(f), C.byref(c))
+                assert f.value == pos
+                pos += c.value
+                sizes.append(c.value)
+            assert pos == batch and max(sizes) - min(sizes) <= 1
+    f, c = C.c_size_t(5), C.c_size_t(5)
+    ntt.lib.ntt_b200_shard_range(10, 4, 9, C.byref(f), C.byref(c))      # index out of range: empty shard
+    assert (f.value, c.value) == (0, 0)
+
+
+def test_multi_gpu_api_fails_loudly_without_a_device(ntt):
+    if ntt.device_count() > 0:
+        import pytest
+        pytest.skip("a GPU is present")
+    import pytest
+    with pytest.raises(ntt.NttError) as e:
+        ntt.MultiPlan(1 << 10, 0x1FFFFFC800001, ntt.min_primitive_root(1 << 10, 0x1FFFFFC800001), [0])
+    assert "no CUDA device" in str(e.value) or "CPU fallback" in str(e.value)
