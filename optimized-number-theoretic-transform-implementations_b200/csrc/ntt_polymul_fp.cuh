@@ -21,8 +21,10 @@
  *           rounded on the fly); inverse stages 12-9 on the product, still in registers -- the thread that holds 16
  *           contiguous coefficients of NTT(a) and NTT(b) holds the same 16 of the product
  *           product -> a's slot, __syncwarp
- *   pass B' inverse stages 8-4 on the product block (16 lanes of the warp, 32 values each; the other half-warp
- *           has no block of its own here)
+ *   pass B' inverse stages 8-4 on the product block.  There is ONE product block per warp where the forward passes
+ *           had two, so the 32-value network of a column group is split over both half-warps: lane (jb, h) loads
+ *           all 32 values, stage 8 pairs positions (2i, 2i+1) -- half h = 0 keeps the sums, half h = 1 the products --
+ *           and stages 7-4 run on each lane's own 16 values (positions 2i + h) with all 32 lanes busy
  *           __syncthreads
  *   pass A' inverse stages 3-0 across the 16 product blocks with the N^-1 stage, thread j = column j; the columns are
  *           pulled into registers, the pair's 32 slots are re-armed with four TMA boxes, results go from registers
@@ -94,6 +96,23 @@ __device__ __forceinline__ void fp_network_fwd2_r4(double (&xa)[16], double (&xb
   fp_fwd_stage2<4, 3, S.coarse[3]>(xa, xb, c, twf);
   fp_fold_mask<4, S.fold_end>(xa, c);
   fp_fold_mask<4, S.fold_end>(xb, c);
+}
+
+/* inverse schedules of this kernel (ntt_fp_schedule.h, FP_SCHED_INV_POLYMUL): WHICH 0 / 1 / 2 = pass A / B / C */
+template <bool Q50, int WHICH>
+struct FpSelPm {
+  static __host__ __device__ constexpr FpPass get()
+  {
+    const FpSchedule &s = FP_SCHED_INV_POLYMUL[Q50];
+    return WHICH == 0 ? s.a : (WHICH == 1 ? s.b : s.c);
+  }
+};
+/* bit i of the result = bit 2i of a 32-position mask (the masks of the split pass B are symmetric in 2i / 2i+1) */
+__host__ __device__ constexpr uint32_t pm_half_mask(uint32_t m)
+{
+  uint32_t r = 0;
+  for(int i = 0; i < 16; i++) r |= ((m >> (2 * i)) & 1u) << i;
+  return r;
 }
 
 template <bool Q50>
@@ -228,7 +247,7 @@ __global__ void __launch_bounds__(PolymulCfg::T, 1)
         xa[i]          = fp_mul<false>(a, b, __dmul_rn(b, c.qinv), c);
       }
       const double2 *twi = g_cti + (size_t)warp * 32 + lane;
-      fp_network_inv<4, false, FpSel<1, Q50, L, 2>>(xa, c, p, [&](int t) { return __ldg(twi + (size_t)t * groups); });
+      fp_network_inv<4, false, FpSelPm<Q50, 2>>(xa, c, p, [&](int t) { return __ldg(twi + (size_t)t * groups); });
 #pragma unroll
       for(int cc = 0; cc < 8; cc++) {
         ulonglong2 v;
@@ -239,19 +258,46 @@ __global__ void __launch_bounds__(PolymulCfg::T, 1)
     }
     __syncwarp();
 
-    /* ---- pass B, inverse, on the product block (half of the warp: the other half-warp has no block here) ---- */
-    if(hb == 0) {
-      uint8_t *      base = ring_ptr + slot_a * 4096u + ((jb & 1u) << 3);
-      const uint32_t jc   = jb >> 1;
-      const double2 *tw   = tw_i + (PB - 1) + warp * 31;
-      double         x[32];
+    /* ---- pass B, inverse, on the product block, split over both half-warps (see the header) ---------------------- */
+    {
+      constexpr FpPass SB   = FpSelPm<Q50, 1>::get();
+      uint8_t *        base = ring_ptr + slot_a * 4096u + ((jb & 1u) << 3);
+      const uint32_t   jc   = jb >> 1;
+      const double2 *  tw   = tw_i + (PB - 1) + warp * 31;
+      double           xin[32], x[16];
 #pragma unroll
       for(int kk = 0; kk < 32; kk++)
-        x[kk] = *reinterpret_cast<const double *>(base + kk * 128 + ((jc ^ (uint32_t)(kk & 7)) << 4));
-      fp_network_inv<5, false, FpSel<1, Q50, L, 1>>(x, c, p, [&](int t) { return tw[t]; });
+        xin[kk] = *reinterpret_cast<const double *>(base + kk * 128 + ((jc ^ (uint32_t)(kk & 7)) << 4));
+      fp_fold_mask<5, SB.fold_before[0]>(xin, c);
+      if(hb == 0) {
 #pragma unroll
-      for(int kk = 0; kk < 32; kk++)
-        *reinterpret_cast<double *>(base + kk * 128 + ((jc ^ (uint32_t)(kk & 7)) << 4)) = x[kk];
+        for(int i = 0; i < 16; i++) x[i] = __dadd_rn(xin[2 * i], xin[2 * i + 1]);
+      } else {
+#pragma unroll
+        for(int i = 0; i < 16; i++) {
+          const double2 t  = tw[15 + i]; /* network stage u = 4: sub-block i uses twiddle 2^4 - 1 + i */
+          const double  df = __dadd_rn(xin[2 * i], -xin[2 * i + 1]);
+          x[i] = ((SB.coarse[0] >> (2 * i)) & 1u) ? fp_mul<true>(df, t.x, t.y, c) : fp_mul<false>(df, t.x, t.y, c);
+        }
+      }
+      /* stages 1..4 of the 5-stage network on positions 2i + h = stages 0..3 of a 4-stage network on i, same
+       * twiddle indices (the sub-block of position 2i + h at distance 2^s is the sub-block of i at 2^(s-1)) */
+      auto twf = [&](int t) { return tw[t]; };
+      fp_fold_mask<4, pm_half_mask(SB.fold_before[1])>(x, c);
+      fp_inv_stage<4, 0, pm_half_mask(SB.coarse[1]), false>(x, c, p, twf);
+      fp_fold_mask<4, pm_half_mask(SB.fold_before[2])>(x, c);
+      fp_inv_stage<4, 1, pm_half_mask(SB.coarse[2]), false>(x, c, p, twf);
+      fp_fold_mask<4, pm_half_mask(SB.fold_before[3])>(x, c);
+      fp_inv_stage<4, 2, pm_half_mask(SB.coarse[3]), false>(x, c, p, twf);
+      fp_fold_mask<4, pm_half_mask(SB.fold_before[4])>(x, c);
+      fp_inv_stage<4, 3, pm_half_mask(SB.coarse[4]), false>(x, c, p, twf);
+      fp_fold_mask<4, pm_half_mask(SB.fold_end)>(x, c);
+      __syncwarp(); /* every lane has read all 32 positions before any of them is overwritten */
+#pragma unroll
+      for(int i = 0; i < 16; i++) {
+        const uint32_t kk = 2u * i + hb;
+        *reinterpret_cast<double *>(base + kk * 128 + ((jc ^ (kk & 7u)) << 4)) = x[i];
+      }
     }
     __syncthreads();
 
@@ -268,7 +314,7 @@ __global__ void __launch_bounds__(PolymulCfg::T, 1)
       } else {
         named_arrive(T);
       }
-      fp_network_inv<4, true, FpSel<1, Q50, L, 0>>(x, c, p, [&](int t) { return tw_i[t]; });
+      fp_network_inv<4, true, FpSelPm<Q50, 0>>(x, c, p, [&](int t) { return tw_i[t]; });
       uint64_t *gout = p_out + (pair << L);
 #pragma unroll
       for(int b = 0; b < PB; b++) gout[(size_t)b * 512 + tid] = fp_to_u64(x[b], c, p.q);

@@ -1,29 +1,28 @@
 /*
  * csrc/ntt_ring_fp.cuh -- the ring kernel with the butterflies on the FP64 pipe (q <= 2^50 - 2048).
  *
- * Why: on B200 the integer butterfly of ntt_device.cuh costs about 32 SM-cycles per warp (five 32x32->64
- * products dominate), while DFMA/DADD/DMUL issue at 61 lanes/clk/SM.  An exact FP64 formulation needs 8
- * FP64 instructions per butterfly plus 3 per coefficient per pass, and measures 1.33x the integer rate in the
- * register-only microbenchmark (tools/ubench_mix.cu, profiles/r01_ubench_mix.txt).  The two do not overlap
- * (they share issue bandwidth), so the whole network runs in FP64.
+ * Why: on B200 the integer butterfly of ntt_device.cuh costs about 30 issue slots per warp (five 32x32->64
+ * products dominate), the exact FP64 formulation below 8 FP64 instructions = 16 issue slots (an FP64 instruction
+ * holds the scheduler's dispatch port for two cycles and nothing co-issues with it: tools/ubench_rf.cu,
+ * profiles/r02_ubench_rf.txt).  Integer and FP64 work do not overlap, so the whole network runs in FP64.
  *
  * Exactness.  Coefficients are integers held in doubles, signed, |v| < 2^53.  For a twiddle w in [0,q) with
- * winv = RN(w/q) and any integer y:
- *     c = rint(y*winv)                      (magic-constant rounding: c is an integer near w*y/q)
+ * winv = RN(w/q) (within 2^-54 of w/q) and any integer y:
+ *     c = (y*winv + M) - M                  (one fused rounding of y*w/q: to an integer, M = 1.5*2^52, |y*winv| < 2^51
+ *                                            -- "plain" -- or to an EVEN integer, M = 3*2^52, |y*winv| < 2^52 -- "coarse")
  *     h = RN(w*y),  l = fma(w, y, -h)       (error-free product: w*y = h + l exactly)
  *     d = fma(-c, q, h)                     (exact: |h - c*q| < 2^53)
  *     t = d + l                             (exact)  =>  t = w*y - c*q == w*y (mod q), an integer
- * so the residue is exact whatever c is; rounding only decides how large |t| gets.  winv is within 2^-54 of
- * w/q, so |t| <= q*(1/2 + |y|*2^-54) for fp_mul (one fused rounding to an integer) and
- * |t| <= q*(1/2 + min(|y|*2^-53, 1/4) + |y|*2^-54) < q for fp_mul_wide (|y| < 2^52) -- as long as c really is
- * an integer (tests/test_fp64_arith_model.py replays both and the schedules below on the CPU).
- * Butterflies are X' = X + t, Y' = X - t
- * (forward) and X' = X + Y, Y' = t(X - Y) (inverse) with no range correction; every pass first folds its
- * inputs to |v| <= q/2 + 6 (v - rint(v/q)*q, 3 instructions) unless the bounds show it is not needed.  For
- * q <= 2^49 - 1024 the forward transform folds twice (before its middle pass and at the very end; a product
- * needs its operand below 4q = 2^51, or 8q with fp_mul_wide); the inverse, whose sums double per stage, folds
- * every three to four stages.  2^49 - 1024 < q <= 2^50 - 2048 runs a second, more conservative schedule.  See
- * fp_network for the numbers.
+ * so the residue is exact whatever c is; rounding only decides how large |t| gets:
+ *     plain  |t| <= q*(1/2 + |y|*2^-54)          coarse  |t| <= q*(1 + |y|*2^-54)
+ * Butterflies are X' = X + t, Y' = X - t (forward) and X' = X + Y, Y' = t(X - Y) (inverse) with no range
+ * correction; a fold (v - rint(v/q)*q, 3 instructions) brings a value back to |v| <= q/2 + 6.  WHERE values are
+ * folded and WHICH rounding a product uses is not written here: tools/gen_fp_schedule.py derives it with exact
+ * rational bound propagation -- per stage for the forward transform, per POSITION of the register network for the
+ * inverse, whose sums double while its products come back small -- and writes the tables of ntt_fp_schedule.h that
+ * the networks below are instantiated from.  tests/test_fp64_arith_model.py re-checks the tables and the primitives
+ * on the CPU (exact FMA emulation), tests/test_gpu_soak.py compares every row of 64 x 4096-polynomial batches per
+ * modulus class and direction with the oracle.
  * The last pass folds, adds q to negatives and converts back to u64: the output is the canonical residue in
  * [0,q), bit-identical to fwd_ntt_ref_harvey / inv_ntt_ref_harvey (include/ntt_reference.h:19-31,
  * src/ntt_reference.c:33-66).

@@ -58,7 +58,7 @@ static int cuda_error(const char *where)
 
 const char *ntt_b200_last_error(void) { return g_error; }
 int         ntt_b200_device_count(void) { return ntt_cuda_device_count(); }
-const char *ntt_b200_version(void) { return "ntt_b200 0.1 sm_100a"; }
+const char *ntt_b200_version(void) { return "ntt_b200 0.2 sm_100a"; }
 
 int ntt_b200_configure(const char *key, int value)
 {

@@ -199,6 +199,22 @@ def test_schedules_stay_inside_their_limits(schedules, q50, q):
         assert check_inverse_pass(pn, bb, q, False) < P53    # chunk of a larger transform: folded afterwards
 
 
+@pytest.mark.parametrize("q50,q", [(0, (1 << 49) - 1025), (0, 0x1fffffc800001), (0, 7681), (1, (1 << 50) - 2049)])
+def test_polymul_inverse_schedule(schedules, q50, q):
+    """Inverse passes of the one-kernel multiply: input = product of two folded values (|p| <= 0.5625 q <= q), pass B
+    split over two lanes -- from its second stage on, positions 2i and 2i+1 must be treated alike."""
+    pc, pb, pa = schedules[("pminv", q50, 13)]
+    fb = F(q, 2) + 6
+    assert q * (F(1, 2) + fb / (1 << 53)) <= F(q) * F(9, 16) + 1      # the product bound the kernel comment states
+    bc = check_inverse_pass(pc, q, q, False)
+    bb = check_inverse_pass(pb, bc, q, False)
+    assert check_inverse_pass(pa, bb, q, True) < q
+    sym = lambda m: all(((m >> (2 * i)) & 1) == ((m >> (2 * i + 1)) & 1) for i in range(16))
+    for s in range(1, 5):
+        assert sym(pb.fold_before[s]) and sym(pb.coarse[s]), s
+    assert sym(pb.fold_end)
+
+
 def emulate_inverse_pass(p, x, tw, q, final, ninv=None, ninv_w=None):
     """The kernel's instruction sequence (fp_network_inv) on doubles; tw[(u, sub)] = twiddle of network stage u."""
     R, n = p.R, 1 << p.R

@@ -89,10 +89,14 @@ def forward_schedule(L, q50):
     return passes
 
 
-def inverse_pass(R, b_in, q, final, cap_out):
+def inverse_pass(R, b_in, q, final, cap_out, paired=False):
     """Position-aware inverse network.  Stage s (processing order) pairs positions at distance d = 2^s.
     final: the last stage is global stage 0, BOTH outputs are products (by N^-1 and N^-1*w) and must come out
-    below q in magnitude because they are converted without another fold -> plain rounding only."""
+    below q in magnitude because they are converted without another fold -> plain rounding only.
+    paired: positions 2i and 2i+1 live in two different lanes that run the same instruction stream from stage 1 on
+    (k_polymul_fp splits its 32-value inverse pass B over both half-warps: stage 0 pairs (2i, 2i+1) across the two
+    lanes, the later stages run on each lane's 16 values), so from stage 1 on every decision is taken jointly for
+    positions 2i and 2i+1 and the masks come out symmetric."""
     n = 1 << R
     fb = float(fold_bound(q)) if isinstance(b_in, float) else fold_bound(q)
     b = [b_in] * n
@@ -101,37 +105,43 @@ def inverse_pass(R, b_in, q, final, cap_out):
         d = 1 << s
         last = final and s == R - 1
         lim = P51 if last else P52
+        joint = paired and s >= 1
         for lo in range(n):
-            if lo & d:
+            if lo & d or (joint and lo & 1):
                 continue
-            hi = lo + d
-            while b[lo] + b[hi] >= lim or b[lo] + b[hi] >= P53:
-                j = lo if b[lo] >= b[hi] else hi
-                if b[j] <= fb:
+            los = (lo, lo + 1) if joint else (lo,)
+            while any(b[l] + b[l + d] >= lim or b[l] + b[l + d] >= P53 for l in los):
+                side = 0 if max(b[l] for l in los) >= max(b[l + d] for l in los) else d
+                if all(b[l + side] <= fb for l in los):
                     return None                      # cannot be scheduled (does not happen for the moduli served)
-                b[j] = fb
-                p.fold_before[s] |= 1 << j
+                for l in los:
+                    b[l + side] = min(b[l + side], fb)
+                    p.fold_before[s] |= 1 << (l + side)
         nb = list(b)
         for lo in range(n):
-            if lo & d:
+            if lo & d or (joint and lo & 1):
                 continue
-            hi = lo + d
-            D = b[lo] + b[hi]
-            if D < P51:
-                t = t_plain(D, q)
-            else:
-                t = t_coarse(D, q)
-                p.coarse[s] |= 1 << lo
-            if last:
-                nb[lo] = nb[hi] = t
-            else:
-                nb[lo], nb[hi] = D, t
+            los = (lo, lo + 1) if joint else (lo,)
+            coarse = any(b[l] + b[l + d] >= P51 for l in los)
+            for l in los:
+                D = b[l] + b[l + d]
+                if coarse:
+                    t = t_coarse(D, q)
+                    p.coarse[s] |= 1 << l
+                else:
+                    t = t_plain(D, q)
+                if last:
+                    nb[l] = nb[l + d] = t
+                else:
+                    nb[l], nb[l + d] = D, t
         b = nb
     if cap_out is not None:
-        for j in range(n):
-            if b[j] > cap_out:
-                b[j] = fb
-                p.fold_end |= 1 << j
+        for j in range(0, n, 2 if paired else 1):
+            js = (j, j + 1) if paired else (j,)
+            if any(b[x] > cap_out for x in js):
+                for x in js:
+                    b[x] = min(b[x], fb)
+                    p.fold_end |= 1 << x
     p.b_out = max(b)
     return p
 
@@ -170,8 +180,40 @@ def inverse_schedule(L, q50):
     return pc, pb, pa, pn
 
 
+def polymul_inverse_schedule(q50):
+    """Inverse passes of k_polymul_fp (N = 2^13): C (4 stages, input = the product of two folded values,
+    |p| <= 0.5625 q, bounded by q here), B split over both half-warps (paired), A (4 stages with the N^-1 stage)."""
+    q = QMAX[q50]
+    best = None
+    steps = list(range(2, 33))
+    for xc in steps:
+        pc = inverse_pass(4, float(q), q, False, xc / 4 * q)
+        if pc is None:
+            continue
+        for xb in steps:
+            pb = inverse_pass(5, pc.b_out, q, False, xb / 4 * q, paired=True)
+            if pb is None:
+                continue
+            pa = inverse_pass(4, pb.b_out, q, True, None)
+            if pa is None or pa.b_out >= 0.999 * q:
+                continue
+            # per thread: pass C once, pass B on 16 of the 32 positions (both lanes run the same stream), pass A once
+            cost = pc.folds() + pb.folds() / 2 + pa.folds()
+            if best is None or cost < best[0]:
+                best = (cost, xc, xb)
+    assert best is not None
+    _, xc, xb = best
+    pc = inverse_pass(4, F(q), q, False, F(xc, 4) * q)
+    pb = inverse_pass(5, pc.b_out, q, False, F(xb, 4) * q, paired=True)
+    pa = inverse_pass(4, pb.b_out, q, True, None)
+    assert pa.b_out < q
+    return pc, pb, pa
+
+
 def all_schedules():
     out = {}
+    for q50 in (0, 1):
+        out[("pminv", q50, 13)] = list(polymul_inverse_schedule(q50))
     for q50 in (0, 1):
         for L in (12, 13, 14):
             out[("fwd", q50, L)] = forward_schedule(L, q50)
@@ -225,6 +267,14 @@ def render():
                 lines.append("    {%s,\n     %s,\n     %s}," % (pass_txt(a), pass_txt(b), pass_txt(c)))
             lines.append("  },")
         lines.append("};")
+    lines.append("/* inverse passes of the one-kernel multiply (N = 2^13); pass B is split over both half-warps: from its")
+    lines.append(" * second stage on the masks are symmetric in positions 2i / 2i+1 */")
+    lines.append("constexpr FpSchedule FP_SCHED_INV_POLYMUL[2] = {")
+    for q50 in (0, 1):
+        c, b, a = sch[("pminv", q50, 13)]
+        lines.append("  /* Q50=%d */" % q50)
+        lines.append("  {%s,\n   %s,\n   %s}," % (pass_txt(a), pass_txt(b), pass_txt(c)))
+    lines.append("};")
     lines.append("}  // namespace nttb200")
     return "\n".join(lines) + "\n"
 
@@ -237,5 +287,5 @@ if __name__ == "__main__":
         sys.exit(0 if ok else 1)
     with open(HEADER, "w") as fh:
         fh.write(txt)
-    for k, ps in sorted(all_schedules().items()):
+    for k, ps in sorted(all_schedules().items(), key=lambda kv: str(kv[0])):
         print(k, [(p.R, p.folds(), float(p.b_out / QMAX[k[1]])) for p in ps])
