@@ -77,6 +77,7 @@ __device__ __forceinline__ uint64_t fp_to_u64(double v, const FpC &c, uint64_t q
   const uint32_t hi  = (uint32_t)__double2hiint(t), lo = (uint32_t)__double2loint(t);
   const uint32_t qlo = lo32(q), qhi = hi32(q);
   uint32_t       rlo, rhi;
+  /* (a predicated 64-bit add of q instead of the two selects is one instruction shorter and measured 1.7 % slower) */
   asm("{\n\t"
       ".reg .pred p;\n\t"
       ".reg .u32 alo, ahi;\n\t"

@@ -116,6 +116,13 @@ int ring_fp_launch_multi_14(bool fwd, int device, const ntt_cuda_params_t *const
              : ring_fp_launch_multi_one<false, false>(device, plist, n_limbs, polys_per_limb, tm, tm2, (unsigned)grid, d_a, n_chunks, st);
 }
 }  // namespace nttb200
+#elif NTT_RING_L == 14
+namespace nttb200 {
+int ring_fp_launch_multi_14(bool, int, const ntt_cuda_params_t *const *, size_t, size_t, uint64_t *, cudaStream_t)
+{
+  return nl_fail_msg("experiment build: the multi-plan launch is not compiled");
+}
+}  // namespace nttb200
 #endif
 
 #if defined(NTT_RING_TRACE) && NTT_RING_L == 14
