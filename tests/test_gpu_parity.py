@@ -569,3 +569,32 @@ def test_error_behaviour(ntt, oracle, case_tables):
         fwd_only.inv(d, 1)
     fwd_only.fwd(d, 0)  # empty batch is a no-op
     fwd_only.close()
+
+
+@pytest.mark.parametrize("bits", [50, 58])
+def test_maximum_size(ntt, oracle, bits):
+    """N = 2^24, the largest size the C-ABI accepts (NTT_B200_MAX_LOGN): two strided passes + the chunk kernel.
+    bits = 50: FP64 ring kernel; 58: the exact (Harvey) path.  One polynomial against the oracle, forward over the
+    full lazy contract, and the round trip."""
+    m = 24
+    N = 1 << m
+    q = (1 << bits) - ((1 << bits) - 1) % (2 * N)
+    while not oracle.is_prime(q) or (bits == 50 and q > (1 << 50) - 2048):
+        q -= 2 * N
+    x = 2
+    while True:
+        psi = oracle.powmod(x, (q - 1) // (2 * N), q)
+        if oracle.powmod(psi, N, q) == q - 1:
+            break
+        x += 1
+    t = CaseTables(oracle, m, q, psi, oracle.invmod(psi, q), oracle.invmod(N, q))
+    plan = ntt.Plan.from_psi(N, q, psi)
+    a = oracle.uniform(N, min(4 * q, 1 << 64) - 1, 2424)
+    a[:4096] = min(4 * q, 1 << 64) - 2
+    d = to_dev(a)
+    plan.fwd(d, 1)
+    f = to_host(d)
+    assert np.array_equal(f, oracle.fwd(a, q, t.w, t.w_con))
+    plan.inv(d, 1)
+    assert np.array_equal(to_host(d), a % np.uint64(q))
+    plan.close()
