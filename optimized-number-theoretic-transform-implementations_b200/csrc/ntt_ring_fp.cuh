@@ -22,7 +22,7 @@
  * inverse, whose sums double while its products come back small -- and writes the tables of ntt_fp_schedule.h that
  * the networks below are instantiated from.  tests/test_fp64_arith_model.py re-checks the tables and the primitives
  * on the CPU (exact FMA emulation), tests/test_gpu_soak.py compares every row of 64 x 4096-polynomial batches per
- * modulus class and direction with the oracle.
+ * modulus class and direction with the CPU restatement of the reference.
  * The last pass folds, adds q to negatives and converts back to u64: the output is the canonical residue in
  * [0,q), bit-identical to fwd_ntt_ref_harvey / inv_ntt_ref_harvey (include/ntt_reference.h:19-31,
  * src/ntt_reference.c:33-66).
