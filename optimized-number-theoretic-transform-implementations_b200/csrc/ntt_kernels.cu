@@ -901,8 +901,9 @@ static int dispatch_strided(int device, int R, const ntt_cuda_params_t &p, uint6
 }
 
 /* k_strided_multi with two adjacent groups per thread (see k_strided_v2) */
+/* (R <= 2: capped at 64 registers -- four resident CTAs; at 70 registers the forward pass ran at 5.0 instead of 5.9 TB/s) */
 template <int R, bool FWD, int OUT>
-__global__ void __launch_bounds__(256) k_strided_multi_v2(const __grid_constant__ RingLimbs<true> limbs,
+__global__ void __launch_bounds__(256, R <= 2 ? 4 : 1) k_strided_multi_v2(const __grid_constant__ RingLimbs<true> limbs,
                                                           uint64_t *__restrict__ a, uint32_t s0, size_t n_groups)
 {
   constexpr int  n      = 1 << R;

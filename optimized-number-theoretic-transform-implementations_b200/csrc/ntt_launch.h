@@ -31,10 +31,12 @@ template <bool MULTI>
 struct RingLimbs {
   ntt_cuda_params_t e[MULTI ? RING_MAX_LIMBS : 1];
   uint32_t          polys_per_limb;
+  uint32_t          ctas_per_limb; /* ring kernel: the grid is limbs x ctas_per_limb, a CTA serves one limb */
 };
 template <>
 struct RingLimbs<false> {
   uint32_t polys_per_limb;
+  uint32_t ctas_per_limb;
 };
 
 /* what the forward ring kernel may be asked to do on top of the transform */

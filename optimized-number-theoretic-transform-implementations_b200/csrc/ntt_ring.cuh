@@ -82,21 +82,69 @@ __device__ __forceinline__ void fence_proxy_async()
 {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+/* L2 residency (north star: twiddle tables "kept L2-resident"): the coefficient stream is read once and written once,
+ * so its TMA loads and stores carry an evict-first policy, and the per-thread twiddle loads of the last pass an
+ * evict-last one -- the tables (1 MiB per plan and direction) then survive the 128 KiB-per-transform stream in the
+ * 126 MB L2 whatever the batch size.  Measured (profiles/r02g_*): with ONE plan the tables stay resident anyway and
+ * the hinted table load costs the forward kernel 2 % (one more register pair and a volatile load in a schedule that is
+ * sensitive to both), so single-plan kernels hint the stream only; with 48 plans in one launch (RNS limbs, 47 MB of
+ * last-pass tables in flight) 60 % of the table reads missed L2 and came from DRAM -- there the table loads carry the
+ * keep policy too.  -DNTT_L2HINT=0 builds without any hint (A/B timing). */
+#ifndef NTT_L2HINT
+#define NTT_L2HINT 1
+#endif
+__device__ __forceinline__ uint64_t l2_policy_stream()
+{
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_keep()
+{
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+/* 16-byte read-only load of a table entry with the keep policy */
+__device__ __forceinline__ double2 ldg_keep(const double2 *ptr)
+{
+#if NTT_L2HINT
+  double2 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(ptr), "l"(l2_policy_keep()));
+  return v;
+#else
+  return __ldg(ptr);
+#endif
+}
 /* global -> shared tile load (box {32 x u32, 32 rows} = 4 KiB), completion counted on `bar` */
 __device__ __forceinline__ void tma_load_block(uint32_t dst, const CUtensorMap *tm, int row, uint32_t bar)
 {
+#if NTT_L2HINT
+  asm volatile(
+    "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::
+      "r"(dst),
+    "l"(tm), "r"(0), "r"(row), "r"(bar), "l"(l2_policy_stream())
+    : "memory");
+#else
   asm volatile(
     "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
       "r"(dst),
     "l"(tm), "r"(0), "r"(row), "r"(bar)
     : "memory");
+#endif
 }
 /* shared -> global tile store, tracked by the issuing thread's bulk async-group */
 __device__ __forceinline__ void tma_store_block(const CUtensorMap *tm, int row, uint32_t src)
 {
+#if NTT_L2HINT
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%1, %2}], [%3], %4;" ::"l"(tm),
+               "r"(0), "r"(row), "r"(src), "l"(l2_policy_stream())
+               : "memory");
+#else
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tm), "r"(0),
                "r"(row), "r"(src)
                : "memory");
+#endif
 }
 __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 /* all of this thread's store groups have finished READING shared memory (slots may be overwritten) */

@@ -254,10 +254,12 @@ enum { RING_PLAIN = 0, RING_MUL = 1, RING_LAZY = 2 };
 /*
  * MULTI: one launch over the chunks of SEVERAL plans (RNS limbs: same N, one modulus and one set of tables each;
  * limb l owns polys_per_limb consecutive polynomials of the array).  The per-limb parameters travel as a kernel
- * argument (constant bank, indexed by the limb of the chunk at hand); a CTA works on a CONTIGUOUS range of the
- * chunk sequence ordered (chunk-in-polynomial, limb, polynomial), so that the limb -- and with it the twiddle
- * cache -- changes a couple of times per CTA at most.  One launch gives every CTA dozens of chunks to pipeline
- * where a launch per limb gives it three or four.
+ * argument (constant bank).  Every CTA serves ONE limb for its whole life: the grid is (ctas_per_limb, limbs), CTA
+ * (x, y) belongs to limb y and takes every ctas_per_limb-th chunk of that limb in the order
+ * (chunk-in-polynomial, polynomial), so its twiddle cache changes 2^(logn-14) times.  The limb index is blockIdx.y, which lets q and 1/q live in uniform registers like in the single-plan kernel (with a limb index
+ * that changed inside the loop they sat in ordinary registers and 288 of the 801 DFMAs per thread paid for a third
+ * register operand).  One launch gives every CTA dozens of chunks to pipeline where a launch per limb gives it three
+ * or four.
  */
 template <bool MULTI>
 __device__ __forceinline__ const ntt_cuda_params_t &ring_plan_of(const ntt_cuda_params_t &p0, const RingLimbs<MULTI> &limbs,
@@ -295,27 +297,35 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t s1        = p0.logn - L;
-  /* which chunks this CTA works on: every gridDim-th chunk (single plan), or a contiguous range of the sequence
-   * ordered (chunk-in-polynomial, limb, polynomial) (several plans) */
-  const uint32_t n_polys_all = (uint32_t)(n_chunks >> s1);
-  const size_t   range_lo  = MULTI ? (size_t)blockIdx.x * n_chunks / gridDim.x : 0;
-  const size_t   range_hi  = MULTI ? (size_t)(blockIdx.x + 1) * n_chunks / gridDim.x : 0;
-  const size_t   my_polys  = MULTI ? range_hi - range_lo
+  /* which chunks this CTA works on: every gridDim-th chunk (single plan), or every ctas_per_limb-th chunk of its limb
+   * in the order (chunk-in-polynomial, polynomial) (several plans) */
+  uint32_t my_limb = 0, cta_in_limb = 0, cpl = 1, ppl = 1;
+  if constexpr(MULTI) {
+    cpl         = limbs.ctas_per_limb;
+    ppl         = limbs.polys_per_limb;
+    my_limb     = blockIdx.y; /* grid (ctas_per_limb, limbs): no division, the index stays on the uniform datapath */
+    cta_in_limb = blockIdx.x;
+  }
+  const uint32_t limb_chunks = ppl << s1; /* MULTI: chunks of one limb */
+  const size_t   my_polys  = MULTI ? (limb_chunks > cta_in_limb ? (limb_chunks - cta_in_limb + cpl - 1) / cpl : 0)
                                    : ((n_chunks > blockIdx.x) ? (n_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0);
   auto chunk_of = [&](size_t k) -> size_t {
     if(!MULTI) return blockIdx.x + k * gridDim.x;
-    const uint32_t i = (uint32_t)(range_lo + k), cpv = i / n_polys_all, rest = i - cpv * n_polys_all;
-    return ((size_t)rest << s1) + cpv;
+    const uint32_t i = cta_in_limb + (uint32_t)k * cpl, cpv = i / ppl, rest = i - cpv * ppl;
+    return ((size_t)(my_limb * ppl + rest) << s1) + cpv;
   };
   const size_t   my_blocks = my_polys * NB;
   const size_t   groups    = (size_t)1 << (p0.logn - 4);
   /* single plan: the constants of the transform are loop invariants (kept out of the loop by hand: hoisting them
    * from inside changed the schedule of the headline kernel by half a percent) */
-  const FpC      c0{p0.q_fd, p0.qinv_fd, NTT_FP_MAGIC};
-  const double   in_bias0 = -(4503599627370496.0 + (FWD ? 2.0 * p0.q_fd : p0.q_fd));
-  const double   q_bias0  = NTT_FP_MAGIC + p0.q_fd;
-  const double2 *g_fd0    = (const double2 *)(FWD ? p0.fwd_fd : p0.inv_fd);
-  const double2 *g_ct0    = (const double2 *)(FWD ? p0.fwd_ct_fd : p0.inv_ct_fd);
+  /* the plan of this CTA: the kernel's own (single plan), or its limb's entry of the argument table */
+  const ntt_cuda_params_t &p = ring_plan_of<MULTI>(p0, limbs, my_limb);
+  const FpC      c{p.q_fd, p.qinv_fd, NTT_FP_MAGIC};
+  /* the conversion centres the input: forward [0,4q) -> [-2q,2q), inverse [0,2q) -> [-q,q) */
+  const double   in_bias = -(4503599627370496.0 + (FWD ? 2.0 * p.q_fd : p.q_fd));
+  const double   q_bias  = NTT_FP_MAGIC + p.q_fd; /* lazy output: v + q lands in (0, 2q) */
+  const double2 *g_fd    = (const double2 *)(FWD ? p.fwd_fd : p.inv_fd);
+  const double2 *g_ct    = (const double2 *)(FWD ? p.fwd_ct_fd : p.inv_ct_fd);
 
   auto slot_addr  = [&](size_t g) -> uint32_t { return ring + (uint32_t)(g % SLOTS) * 4096u; };
   auto issue_load = [&](size_t g) {
@@ -364,17 +374,7 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
   for(size_t k = 0; k < my_polys; k++) {
     const size_t   chunk = MULTI ? chunk_of(k) : blockIdx.x + k * gridDim.x;
     const uint32_t cp    = (uint32_t)(chunk & (((size_t)1 << s1) - 1));
-    uint32_t       limb  = 0;
-    if constexpr(MULTI) limb = (uint32_t)(chunk >> s1) / limbs.polys_per_limb;
-    /* the plan of this chunk: the kernel's own (single plan), or the limb's entry of the argument table */
-    const ntt_cuda_params_t &p = ring_plan_of<MULTI>(p0, limbs, limb);
-    const FpC      c = MULTI ? FpC{p.q_fd, p.qinv_fd, NTT_FP_MAGIC} : c0;
-    /* the conversion centres the input: forward [0,4q) -> [-2q,2q), inverse [0,2q) -> [-q,q) */
-    const double   in_bias = MULTI ? -(4503599627370496.0 + (FWD ? 2.0 * p.q_fd : p.q_fd)) : in_bias0;
-    const double   q_bias = MULTI ? NTT_FP_MAGIC + p.q_fd : q_bias0; /* lazy output: v + q lands in (0, 2q) */
-    const double2 *g_fd  = MULTI ? (const double2 *)(FWD ? p.fwd_fd : p.inv_fd) : g_fd0;
-    const double2 *g_ct  = MULTI ? (const double2 *)(FWD ? p.fwd_ct_fd : p.inv_ct_fd) : g_ct0;
-    const uint32_t cache_key = MULTI ? ((limb << 8) | cp) : cp;
+    const uint32_t cache_key = cp;
     if(cache_key != cached_cp) {
       __syncthreads();
       for(uint32_t e = tid; e < (uint32_t)C::NTW; e += T) {
@@ -514,7 +514,11 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
       }
       const double2 *tw = g_ct + ((size_t)cp * NB + blk) * 32 + lane;
       const double2 *tw0 = tw_s + C::NTW + blk * 32 + lane;
-      auto           twf = [&](int t) { return (TWC0 && t == 0) ? *tw0 : __ldg(tw + (size_t)t * groups); };
+      auto           twf = [&](int t) {
+        if(TWC0 && t == 0) return *tw0;
+        if constexpr(MULTI) return ldg_keep(tw + (size_t)t * groups); /* many plans: pin the tables in L2 (ntt_ring.cuh) */
+        else return __ldg(tw + (size_t)t * groups);
+      };
       if constexpr(FWD) {
         fp_network_fwd<4, FpSel<0, Q50, L, 2>>(x, c, twf, [&]() {
           /* the first block's store has had this block's loads and two stages of butterflies to drain: its slot is
@@ -604,9 +608,6 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
         __syncwarp(); /* orders the other lanes' pass-B stores before lane 0's releasing arrive */
         if(lane == 0) mbar_arrive(cta_bar);
         bool prerun = k + 1 < my_polys;
-        if constexpr(MULTI) { /* the next chunk must belong to the same plan: pass C runs with this one's constants */
-          if(prerun) prerun = (uint32_t)(chunk_of(k + 1) >> s1) / limbs.polys_per_limb == limb;
-        }
         if(prerun) {
           mbar_wait(bars + 16u * (uint32_t)((k + 1) % C::NBAR), (uint32_t)(((k + 1) / C::NBAR) & 1));
           const size_t nchunk = MULTI ? chunk_of(k + 1) : chunk + gridDim.x;

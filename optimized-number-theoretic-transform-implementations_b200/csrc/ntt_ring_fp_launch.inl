@@ -15,7 +15,7 @@ static int ring_fp_launch_one(int device, const ntt_cuda_params_t &p, const CUte
     NL_CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_FP));
     ready[device & 63] = true;
   }
-  kern<<<grid, C::THREADS, C::SMEM_FP, st>>>(p, tm, tm2, n_chunks, d_a, o.d_other, o.other_mask, RingLimbs<false>{0});
+  kern<<<grid, C::THREADS, C::SMEM_FP, st>>>(p, tm, tm2, n_chunks, d_a, o.d_other, o.other_mask, RingLimbs<false>{0, 1});
   NL_CU(cudaGetLastError());
   return 0;
 }
@@ -89,7 +89,8 @@ static int ring_fp_launch_multi_one(int device, const ntt_cuda_params_t *const *
   static thread_local RingLimbs<true> lb; /* 21 KiB: kept off the stack */
   for(size_t l = 0; l < n_limbs; l++) lb.e[l] = *plist[l];
   lb.polys_per_limb = (uint32_t)polys_per_limb;
-  kern<<<grid, C::THREADS, C::SMEM_FP, st>>>(*plist[0], tm, tm2, n_chunks, d_a, nullptr, ~(size_t)0, lb);
+  lb.ctas_per_limb  = grid / (unsigned)n_limbs;
+  kern<<<dim3(lb.ctas_per_limb, (unsigned)n_limbs), C::THREADS, C::SMEM_FP, st>>>(*plist[0], tm, tm2, n_chunks, d_a, nullptr, ~(size_t)0, lb);
   NL_CU(cudaGetLastError());
   return 0;
 }
@@ -105,9 +106,12 @@ int ring_fp_launch_multi_14(bool fwd, int device, const ntt_cuda_params_t *const
   CUtensorMap tm, tm2;
   if(nl_make_block_tmap(&tm, d_a, n_chunks << 14, 32)) return -1;
   if(nl_make_block_tmap(&tm2, d_a, n_chunks << 14, 32 * C::BOXB)) return -1;
-  size_t grid = (size_t)nl_sm_count(device);
-  if(grid > n_chunks) grid = n_chunks;
-  const bool q50 = p.fp64 == 2;
+  /* a CTA serves one limb: as many CTAs per limb as the SMs allow (at least one, at most one per chunk) */
+  size_t cpl = (size_t)nl_sm_count(device) / n_limbs;
+  if(cpl < 1) cpl = 1;
+  if(cpl > n_chunks / n_limbs) cpl = n_chunks / n_limbs;
+  const size_t grid = cpl * n_limbs;
+  const bool   q50  = p.fp64 == 2;
   if(fwd) {
     return q50 ? ring_fp_launch_multi_one<true, true>(device, plist, n_limbs, polys_per_limb, tm, tm2, (unsigned)grid, d_a, n_chunks, st)
                : ring_fp_launch_multi_one<true, false>(device, plist, n_limbs, polys_per_limb, tm, tm2, (unsigned)grid, d_a, n_chunks, st);
