@@ -256,10 +256,9 @@ enum { RING_PLAIN = 0, RING_MUL = 1, RING_LAZY = 2 };
  * limb l owns polys_per_limb consecutive polynomials of the array).  The per-limb parameters travel as a kernel
  * argument (constant bank).  Every CTA serves ONE limb for its whole life: the grid is (ctas_per_limb, limbs), CTA
  * (x, y) belongs to limb y and takes every ctas_per_limb-th chunk of that limb in the order
- * (chunk-in-polynomial, polynomial), so its twiddle cache changes 2^(logn-14) times.  The limb index is blockIdx.y, which lets q and 1/q live in uniform registers like in the single-plan kernel (with a limb index
- * that changed inside the loop they sat in ordinary registers and 288 of the 801 DFMAs per thread paid for a third
- * register operand).  One launch gives every CTA dozens of chunks to pipeline where a launch per limb gives it three
- * or four.
+ * (chunk-in-polynomial, polynomial), so its twiddle cache changes 2^(logn-14) times and its constants are loop
+ * invariants (see where q and 1/q are read in the kernel).  One launch gives every CTA dozens of chunks to pipeline
+ * where a launch per limb gives it three or four.
  */
 template <bool MULTI>
 __device__ __forceinline__ const ntt_cuda_params_t &ring_plan_of(const ntt_cuda_params_t &p0, const RingLimbs<MULTI> &limbs,
@@ -320,7 +319,23 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
    * from inside changed the schedule of the headline kernel by half a percent) */
   /* the plan of this CTA: the kernel's own (single plan), or its limb's entry of the argument table */
   const ntt_cuda_params_t &p = ring_plan_of<MULTI>(p0, limbs, my_limb);
-  const FpC      c{p.q_fd, p.qinv_fd, NTT_FP_MAGIC};
+  /* q and 1/q feed one operand of 288 of the forward kernel's 801 DFMAs.  Read as limbs.e[my_limb].q_fd they come out
+   * of an indexed constant-bank load into ORDINARY registers and those DFMAs pay for a third register operand (3.2
+   * issue cycles instead of 2, tools/ubench_rf.cu); read through a switch whose every case names a fixed table slot,
+   * each load has a constant address, lands in a uniform register and stays there, as in the single-plan kernel. */
+  double q_sel = p0.q_fd, qinv_sel = p0.qinv_fd;
+  if constexpr(MULTI) {
+    static_assert(RING_MAX_LIMBS == 48, "the switch below enumerates the table slots");
+    switch(my_limb) {
+#define NTT_SEL(i) case i: q_sel = limbs.e[i].q_fd; qinv_sel = limbs.e[i].qinv_fd; break;
+#define NTT_SEL8(b) NTT_SEL(b) NTT_SEL(b + 1) NTT_SEL(b + 2) NTT_SEL(b + 3) NTT_SEL(b + 4) NTT_SEL(b + 5) NTT_SEL(b + 6) NTT_SEL(b + 7)
+      NTT_SEL8(0) NTT_SEL8(8) NTT_SEL8(16) NTT_SEL8(24) NTT_SEL8(32) NTT_SEL8(40)
+#undef NTT_SEL8
+#undef NTT_SEL
+      default: break;
+    }
+  }
+  const FpC      c{q_sel, qinv_sel, NTT_FP_MAGIC};
   /* the conversion centres the input: forward [0,4q) -> [-2q,2q), inverse [0,2q) -> [-q,q) */
   const double   in_bias = -(4503599627370496.0 + (FWD ? 2.0 * p.q_fd : p.q_fd));
   const double   q_bias  = NTT_FP_MAGIC + p.q_fd; /* lazy output: v + q lands in (0, 2q) */

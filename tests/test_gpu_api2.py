@@ -285,7 +285,8 @@ def test_one_kernel_polymul(ntt, oracle, bits, batch):
     plan.close()
 
 
-@pytest.mark.parametrize("m,limbs,per,bits", [(16, 5, 3, 50), (14, 4, 9, 49), (15, 48, 2, 50), (17, 3, 1, 49)])
+@pytest.mark.parametrize("m,limbs,per,bits", [(16, 5, 3, 50), (14, 4, 9, 49), (15, 48, 2, 50), (17, 3, 1, 49),
+                                               (14, 48, 1, 49), (14, 2, 200, 49), (15, 7, 33, 50)])
 def test_rns_single_launch_matches_oracle_and_per_limb_path(ntt, oracle, m, limbs, per, bits):
     """RNS batches of N >= 2^14 in the FP64 range run as ONE launch per kernel over all limbs (k_ring_fp<.., MULTI>,
     k_strided_multi): every limb equals the oracle with its own modulus, the inverse returns the input, and the
