@@ -781,6 +781,20 @@ static bool use_fp64(const ntt_cuda_params_t &p, bool fwd)
   return fp64_enabled() && p.fp64 && (fwd ? p.fwd_ct_fd : p.inv_ct_fd) != nullptr;
 }
 
+/* Does the chunk stage of this transform run on the FP64 ring kernel (same conditions as try_ring)?  Then the strided
+ * passes around it run in FP64 too (ntt_strided_fp.cuh): they exchange canonical residues with it.
+ * NTT_B200_NO_FP_STRIDED=1 keeps the integer passes (A/B timing). */
+static bool fp_strided_path(const ntt_cuda_params_t &p, int L, const uint64_t *d_a, bool fwd)
+{
+  static int on = -1;
+  if(on < 0) {
+    const char *e = getenv("NTT_B200_NO_FP_STRIDED");
+    on            = (e && e[0] == '1') ? 0 : 1;
+  }
+  return on && ring_enabled() && p.lazy && L >= 12 && L <= 14 && use_fp64(p, fwd) && (fwd ? p.fwd_ct_wu : p.inv_ct_wu) &&
+         (fwd ? p.fwd_fd : p.inv_fd) && ((uintptr_t)d_a & 127) == 0;
+}
+
 /* Several small launches run side by side (RNS limbs on their own streams): each then takes only as many CTAs
  * as gives every CTA a few chunks to pipeline, and leaves the other SMs to its neighbours.  0 = whole GPU. */
 static thread_local size_t g_min_chunks_per_cta = 0;
@@ -1063,10 +1077,12 @@ static int forward_impl(int device, const ntt_cuda_params_t &p, uint64_t *d_a, s
   uint32_t    s0 = 0;
   /* the FP64 chunk kernel wants inputs below 2^52: the last strided pass then hands over values below 2q */
   const bool fp_next = !EXACT && ring_enabled() && p.lazy && sp.L >= 12 && use_fp64(p, true) && ((uintptr_t)d_a & 127) == 0;
+  const bool fp_pass = !EXACT && fp_strided_path(p, sp.L, d_a, true);
   for(int k = 0; k < sp.ns; k++) {
     if(phases & PH_STRIDED) {
-      const int rc = (fp_next && k == sp.ns - 1) ? dispatch_strided<true, EXACT, 2>(device, sp.r[k], p, d_a, s0, batch, st)
-                                                 : dispatch_strided<true, EXACT, 0>(device, sp.r[k], p, d_a, s0, batch, st);
+      const int rc = fp_pass ? strided_fp_launch(true, false, sp.r[k], device, p, d_a, s0, batch, st)
+                             : ((fp_next && k == sp.ns - 1) ? dispatch_strided<true, EXACT, 2>(device, sp.r[k], p, d_a, s0, batch, st)
+                                                            : dispatch_strided<true, EXACT, 0>(device, sp.r[k], p, d_a, s0, batch, st));
       if(rc) return -1;
     }
     s0 += sp.r[k];
@@ -1104,11 +1120,13 @@ static int inverse_impl(int device, const ntt_cuda_params_t &p, uint64_t *d_a, s
     if(!done && dispatch_chunk<false, EXACT>(device, sp.L, p, d_a, batch << s1, st)) return -1;
   }
   if(!(phases & PH_STRIDED)) return 0;
-  uint32_t s0 = s1;
+  const bool fp_pass = !EXACT && fp_strided_path(p, sp.L, d_a, false);
+  uint32_t   s0      = s1;
   for(int k = sp.ns - 1; k >= 0; k--) {
     s0 -= sp.r[k];
-    const int rc = (k == 0) ? dispatch_strided<false, EXACT, 1>(device, sp.r[k], p, d_a, s0, batch, st)
-                            : dispatch_strided<false, EXACT, 0>(device, sp.r[k], p, d_a, s0, batch, st);
+    const int rc = fp_pass ? strided_fp_launch(false, k == 0, sp.r[k], device, p, d_a, s0, batch, st)
+                           : ((k == 0) ? dispatch_strided<false, EXACT, 1>(device, sp.r[k], p, d_a, s0, batch, st)
+                                       : dispatch_strided<false, EXACT, 0>(device, sp.r[k], p, d_a, s0, batch, st));
     if(rc) return -1;
   }
   return 0;
@@ -1128,12 +1146,14 @@ extern "C" int ntt_cuda_describe(const ntt_cuda_params_t *p, int inverse, char *
   else snprintf(chunk, sizeof(chunk), "k_chunk<%d,%s,%s>", sp.L, fwd ? "fwd" : "inv", p->lazy ? "lazy" : "exact");
   size_t off = 0;
   buf[0]     = 0;
+  /* (128-byte aligned data assumed, as for the chunk kernel) */
+  const char *sk = fp_strided_path(*p, sp.L, nullptr, fwd) ? "k_strided_fp" : "k_strided";
   if(fwd) {
-    for(int k = 0; k < sp.ns && off < n; k++) off += (size_t)snprintf(buf + off, n - off, "k_strided<%d> + ", sp.r[k]);
+    for(int k = 0; k < sp.ns && off < n; k++) off += (size_t)snprintf(buf + off, n - off, "%s<%d> + ", sk, sp.r[k]);
     if(off < n) off += (size_t)snprintf(buf + off, n - off, "%s", chunk);
   } else {
     if(off < n) off += (size_t)snprintf(buf + off, n - off, "%s", chunk);
-    for(int k = sp.ns - 1; k >= 0 && off < n; k--) off += (size_t)snprintf(buf + off, n - off, " + k_strided<%d>", sp.r[k]);
+    for(int k = sp.ns - 1; k >= 0 && off < n; k--) off += (size_t)snprintf(buf + off, n - off, " + %s<%d>", sk, sp.r[k]);
   }
   if(launches) *launches = sp.ns + 1;
   return 0;
@@ -1471,13 +1491,17 @@ static int rns_multi_launch(int device, const ntt_cuda_params_t *const *plist, s
   for(size_t l = 0; l < limbs; l++) lb.e[l] = *plist[l];
   lb.polys_per_limb = (uint32_t)batch_per_limb;
   const size_t total = limbs * batch_per_limb;
+  /* rns_multi_ok has checked that every limb runs the FP64 chunk kernel: the strided passes can be FP64 as well */
+  bool fp_pass = true;
+  for(size_t l = 0; l < limbs; l++) fp_pass = fp_pass && fp_strided_path(*plist[l], sp.L, d_a, !inverse);
   uint32_t     s1    = 0;
   for(int k = 0; k < sp.ns; k++) s1 += sp.r[k];
   if(!inverse) {
     uint32_t s0 = 0;
     for(int k = 0; k < sp.ns; k++) {
-      const int rc = (k == sp.ns - 1) ? dispatch_strided_multi<true, 2>(device, sp.r[k], lb, d_a, s0, total, st)
-                                      : dispatch_strided_multi<true, 0>(device, sp.r[k], lb, d_a, s0, total, st);
+      const int rc = fp_pass ? strided_fp_launch_multi(true, false, sp.r[k], device, lb, d_a, s0, total, st)
+                             : ((k == sp.ns - 1) ? dispatch_strided_multi<true, 2>(device, sp.r[k], lb, d_a, s0, total, st)
+                                                 : dispatch_strided_multi<true, 0>(device, sp.r[k], lb, d_a, s0, total, st));
       if(rc) return -1;
       s0 += sp.r[k];
     }
@@ -1487,8 +1511,9 @@ static int rns_multi_launch(int device, const ntt_cuda_params_t *const *plist, s
   uint32_t s0 = s1;
   for(int k = sp.ns - 1; k >= 0; k--) {
     s0 -= sp.r[k];
-    const int rc = (k == 0) ? dispatch_strided_multi<false, 1>(device, sp.r[k], lb, d_a, s0, total, st)
-                            : dispatch_strided_multi<false, 0>(device, sp.r[k], lb, d_a, s0, total, st);
+    const int rc = fp_pass ? strided_fp_launch_multi(false, k == 0, sp.r[k], device, lb, d_a, s0, total, st)
+                           : ((k == 0) ? dispatch_strided_multi<false, 1>(device, sp.r[k], lb, d_a, s0, total, st)
+                                       : dispatch_strided_multi<false, 0>(device, sp.r[k], lb, d_a, s0, total, st));
     if(rc) return -1;
   }
   return 0;

@@ -60,6 +60,12 @@ int polymul_fp_launch(int device, const ntt_cuda_params_t &p, uint64_t *d_a, uin
 /* one launch of the L = 14 FP64 ring kernel over the chunks of several plans (same N, same range schedule) */
 int ring_fp_launch_multi_14(bool fwd, int device, const ntt_cuda_params_t *const *plist, size_t n_limbs,
                             size_t polys_per_limb, uint64_t *d_a, cudaStream_t st);
+/* strided passes in FP64 (ntt_strided_fp.cuh): global stages s0 .. s0+R-1 of `batch` polynomials; last: the inverse pass
+ * that ends with global stage 0 (N^-1) */
+int strided_fp_launch(bool fwd, bool last, int R, int device, const ntt_cuda_params_t &p, uint64_t *d_a, uint32_t s0,
+                      size_t batch, cudaStream_t st);
+int strided_fp_launch_multi(bool fwd, bool last, int R, int device, const RingLimbs<true> &lb, uint64_t *d_a, uint32_t s0,
+                            size_t total_polys, cudaStream_t st);
 int ring_int_launch(int L, bool fwd, int device, const ntt_cuda_params_t &p, uint64_t *d_a, size_t n_chunks,
                     cudaStream_t st);
 

@@ -199,6 +199,20 @@ def test_schedules_stay_inside_their_limits(schedules, q50, q):
         assert check_inverse_pass(pn, bb, q, False) < P53    # chunk of a larger transform: folded afterwards
 
 
+@pytest.mark.parametrize("q50,q", [(0, (1 << 49) - 1025), (0, Q49), (0, 0x1fffffc800001), (0, 7681),
+                                   (1, (1 << 50) - 2049), (1, Q50), (1, (1 << 49) - 1023)])
+def test_strided_pass_schedules_stay_inside_their_limits(schedules, q50, q):
+    """k_strided_fp (ntt_strided_fp.cuh): one network of R = 1..5 stages.  Forward input centred to |v| <= 2q, every
+    output folded afterwards; inverse input centred to |v| <= q, either ending with the N^-1 stage (products below q,
+    converted without a fold) or folded afterwards."""
+    for R in range(1, 6):
+        (pf,), (pi,), (pn,) = schedules[("sfwd", q50, R)], schedules[("sinv", q50, R)], schedules[("sinvnf", q50, R)]
+        assert pf.R == pi.R == pn.R == R
+        assert check_forward([pf], q) < P53
+        assert check_inverse_pass(pi, q, q, True) < q
+        assert check_inverse_pass(pn, q, q, False) < P53
+
+
 @pytest.mark.parametrize("q50,q", [(0, (1 << 49) - 1025), (0, 0x1fffffc800001), (0, 7681), (1, (1 << 50) - 2049)])
 def test_polymul_inverse_schedule(schedules, q50, q):
     """Inverse passes of the one-kernel multiply: input = product of two folded values (|p| <= 0.5625 q <= q), pass B

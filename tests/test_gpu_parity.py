@@ -471,6 +471,51 @@ def test_large_n_two_pass_split(ntt, oracle):
     plan.close()
 
 
+@pytest.mark.parametrize("m,bits", [(15, 49), (16, 50), (17, 49), (17, 50), (18, 49), (18, 50), (19, 49), (19, 50),
+                                    (20, 50), (21, 49)])
+def test_fp64_strided_passes_all_radices(ntt, oracle, m, bits):
+    """N = 2^15 .. 2^21 in the FP64 range: the stages above a 2^14 chunk run as k_strided_fp passes of radix 2^1 .. 2^5
+    (one or two passes; 16-byte and 8-byte variants; both range schedules).  Inputs at the edges of the contracts
+    ([0,4q) forward, [0,2q) inverse), three polynomials, every coefficient against the oracle; and the integer strided
+    passes (NTT_B200_NO_FP64-style switch) must give the same bytes."""
+    N = 1 << m
+    top = (1 << bits) - (2048 if bits == 50 else 1024)
+    q = (1 << bits) + 1
+    q -= (q - 1) % (2 * N)
+    while True:
+        q -= 2 * N
+        if q <= top and oracle.is_prime(q):
+            break
+    psi = oracle.min_root(N, q)
+    t = CaseTables(oracle, m, q, psi, oracle.invmod(psi, q), oracle.invmod(N, q))
+    plan = ntt.Plan.from_psi(N, q, psi)
+    assert "k_strided_fp" in plan.describe()[0] and "k_strided_fp" in plan.describe(inverse=True)[0], plan.describe()
+    a = oracle.uniform(3 * N, 4 * q, 700 + m).reshape(3, N)
+    a[0, :8] = [4 * q - 1, 0, 4 * q - 1, 2 * q, q, q - 1, 3 * q + 1, 1]
+    a[1, :] = 4 * q - 1
+    d = to_dev(a)
+    plan.fwd(d, 3)
+    f = to_host(d).reshape(3, N)
+    assert np.array_equal(f, oracle.fwd_batch(a, q, t.w, t.w_con)), "forward"
+    b = oracle.uniform(3 * N, 2 * q, 800 + m).reshape(3, N)
+    b[1, :] = 2 * q - 1
+    d = to_dev(b)
+    plan.inv(d, 3)
+    g = to_host(d).reshape(3, N)
+    assert np.array_equal(g, oracle.inv_batch(b, q, t.n_inv, t.w_inv, t.w_inv_con, t.n_inv_con)), "inverse"
+    try:
+        ntt.configure("fp64", 0)
+        d = to_dev(a)
+        plan.fwd(d, 3)
+        assert np.array_equal(to_host(d).reshape(3, N), f)
+        d = to_dev(b)
+        plan.inv(d, 3)
+        assert np.array_equal(to_host(d).reshape(3, N), g)
+    finally:
+        ntt.configure("fp64", 1)
+    plan.close()
+
+
 def _random_plan_params(oracle, rng, m, bits):
     """A prime q = 1 (mod 2N) of the given width (searched downwards from a random start) and a primitive 2N-th root."""
     N = 1 << m

@@ -210,8 +210,51 @@ def polymul_inverse_schedule(q50):
     return pc, pb, pa
 
 
+def forward_pass_schedule(R, q50):
+    """One forward network of R stages on input centred to |v| <= 2q (a strided pass of a transform larger than a
+    chunk: its input is the caller's [0,4q), or the canonical output of the strided pass before it)."""
+    q = QMAX[q50]
+    p = Pass(R)
+    n = 1 << R
+    b = F(2 * q)
+    for s in range(R):
+        if b >= P52 or (b >= P51 and b + t_coarse(b, q) >= P53):
+            p.fold_before[s] = (1 << n) - 1
+            b = fold_bound(q)
+        if b < P51:
+            b = b + t_plain(b, q)
+        else:
+            p.coarse[s] = (1 << n) - 1
+            b = b + t_coarse(b, q)
+        assert b < P53
+    p.b_out = b
+    return p
+
+
+def strided_schedules(q50):
+    """FP64 strided passes (k_strided_fp): R = 1..5 stages over global memory.  Forward: see forward_pass_schedule; every
+    output is folded and converted to the canonical residue.  Inverse: input = canonical residues (contract [0,2q),
+    centred to |v| <= q); `final`: the pass ends with global stage 0 (N^-1 products, converted without another fold),
+    otherwise every output is folded and converted."""
+    q = QMAX[q50]
+    fwd = [forward_pass_schedule(R, q50) for R in range(1, 6)]
+    inv = [inverse_pass(R, F(q), q, True, None) for R in range(1, 6)]
+    invnf = [inverse_pass(R, F(q), q, False, None) for R in range(1, 6)]
+    for p in inv:
+        assert p is not None and p.b_out < q
+    for p in invnf:
+        assert p is not None and p.b_out < P53
+    return fwd, inv, invnf
+
+
 def all_schedules():
     out = {}
+    for q50 in (0, 1):
+        fwd, inv, invnf = strided_schedules(q50)
+        for R in range(1, 6):
+            out[("sfwd", q50, R)] = [fwd[R - 1]]
+            out[("sinv", q50, R)] = [inv[R - 1]]
+            out[("sinvnf", q50, R)] = [invnf[R - 1]]
     for q50 in (0, 1):
         out[("pminv", q50, 13)] = list(polymul_inverse_schedule(q50))
     for q50 in (0, 1):
@@ -266,6 +309,13 @@ def render():
                     sum(bin(m).count("1") for p in ps for m in p.fold_before) + 16 * 0))
                 lines.append("    {%s,\n     %s,\n     %s}," % (pass_txt(a), pass_txt(b), pass_txt(c)))
             lines.append("  },")
+        lines.append("};")
+    lines.append("/* strided passes in FP64 (k_strided_fp): one network of R = 1..5 stages, indexed [Q50][R-1].  Forward: input centred")
+    lines.append(" * to |v| <= 2q; inverse: input centred to |v| <= q, with / without the N^-1 stage at the end. */")
+    for kind, name in (("sfwd", "FP_SCHED_STRIDED_FWD"), ("sinv", "FP_SCHED_STRIDED_INV"), ("sinvnf", "FP_SCHED_STRIDED_INV_NOFINAL")):
+        lines.append("constexpr FpPass %s[2][5] = {" % name)
+        for q50 in (0, 1):
+            lines.append("  {" + ",\n   ".join(pass_txt(sch[(kind, q50, R)][0]) for R in range(1, 6)) + "},")
         lines.append("};")
     lines.append("/* inverse passes of the one-kernel multiply (N = 2^13); pass B is split over both half-warps: from its")
     lines.append(" * second stage on the masks are symmetric in positions 2i / 2i+1 */")
