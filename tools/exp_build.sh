@@ -14,6 +14,6 @@ done
 wait
 # objects that do not depend on the experiment flags come from the in-tree build
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $OUT/libntt_b200_$name.so $OUT/obj_$name/*.o \
-  $PKG/csrc/ntt_kernels.o $PKG/csrc/ntt_ring_int.o $PKG/csrc/ntt_polymul_fp.o $PKG/host/ntt_math.o $PKG/host/ntt_plan.o $PKG/host/ntt_dropin.o \
+  $PKG/csrc/ntt_kernels.o $PKG/csrc/ntt_ring_int.o $PKG/csrc/ntt_polymul_fp.o $PKG/csrc/ntt_strided_fp.o $PKG/host/ntt_math.o $PKG/host/ntt_plan.o $PKG/host/ntt_dropin.o \
   $PKG/host/ntt_multi.o -Xlinker --version-script=$PKG/exports.map -cudart static -lpthread
 echo built $OUT/libntt_b200_$name.so
