@@ -621,10 +621,13 @@ extern "C" int ntt_cuda_build_tables(int device, const ntt_cuda_params_t *p, con
 __global__ void k_build_fd(const uint64_t *__restrict__ d_w, double2 *__restrict__ fd, double2 *__restrict__ ct,
                            uint32_t logn, uint64_t q)
 {
+  /* multipliers are stored CENTRED, w in (-q/2, q/2): |w/q| <= 1/2 doubles the operand range of the quotient
+   * estimate and halves its error term (ntt_ring_fp.cuh; the residue class is what matters, not the representative) */
   const size_t n  = (size_t)1 << logn;
   const double qd = (double)q;
+  auto centred    = [&](uint64_t w) { return w > (q >> 1) ? -(double)(q - w) : (double)w; }; /* exact: q < 2^50 */
   for(size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const double w = (double)(d_w[i] % q); /* exact: q < 2^49 */
+    const double w = centred(d_w[i] % q);
     fd[i]          = make_double2(w, __ddiv_rn(w, qd));
   }
   if(ct) {
@@ -633,7 +636,7 @@ __global__ void k_build_fd(const uint64_t *__restrict__ d_w, double2 *__restrict
       const uint32_t t = (uint32_t)(i / G);
       const size_t   g = i % G;
       const uint32_t u = 31u - __clz(t + 1u), sub = t + 1u - (1u << u);
-      const double   w = (double)(d_w[((size_t)1 << (logn - 4 + u)) + (g << u) + sub] % q);
+      const double   w = centred(d_w[((size_t)1 << (logn - 4 + u)) + (g << u) + sub] % q);
       ct[i]            = make_double2(w, __ddiv_rn(w, qd));
     }
   }

@@ -6,15 +6,18 @@
  * holds the scheduler's dispatch port for two cycles and nothing co-issues with it: tools/ubench_rf.cu,
  * profiles/r02_ubench_rf.txt).  Integer and FP64 work do not overlap, so the whole network runs in FP64.
  *
- * Exactness.  Coefficients are integers held in doubles, signed, |v| < 2^53.  For a twiddle w in [0,q) with
- * winv = RN(w/q) (within 2^-54 of w/q) and any integer y:
- *     c = (y*winv + M) - M                  (one fused rounding of y*w/q: to an integer, M = 1.5*2^52, |y*winv| < 2^51
- *                                            -- "plain" -- or to an EVEN integer, M = 3*2^52, |y*winv| < 2^52 -- "coarse")
+ * Exactness.  Coefficients are integers held in doubles, signed, |v| < 2^53.  Twiddles are stored centred, w in
+ * (-q/2, q/2), with winv = RN(w/q) (|winv| <= 1/2, within 2^-55 of w/q).  For any integer y:
+ *     c = (y*winv + M) - M                  (one fused rounding of y*w/q: to an integer, M = 1.5*2^52, |y*winv| < 2^51,
+ *                                            i.e. |y| < 2^52 -- "plain" -- or to an EVEN integer, M = 3*2^52,
+ *                                            |y*winv| < 2^52, i.e. |y| < 2^53 -- "coarse")
  *     h = RN(w*y),  l = fma(w, y, -h)       (error-free product: w*y = h + l exactly)
  *     d = fma(-c, q, h)                     (exact: |h - c*q| < 2^53)
  *     t = d + l                             (exact)  =>  t = w*y - c*q == w*y (mod q), an integer
  * so the residue is exact whatever c is; rounding only decides how large |t| gets:
- *     plain  |t| <= q*(1/2 + |y|*2^-54)          coarse  |t| <= q*(1 + |y|*2^-54)
+ *     plain  |t| <= q*(1/2 + |y|*2^-55)          coarse  |t| <= q*(1 + |y|*2^-55)
+ * (a multiplier that is NOT centred -- the data operand of the fused pointwise product -- keeps the older bounds:
+ *  |y*winv| < 2^51 needs |y| < 2^51, error term |y|*2^-54 or, with winv rounded on the fly, |y|*2^-53)
  * Butterflies are X' = X + t, Y' = X - t (forward) and X' = X + Y, Y' = t(X - Y) (inverse) with no range
  * correction; a fold (v - rint(v/q)*q, 3 instructions) brings a value back to |v| <= q/2 + 6.  WHERE values are
  * folded and WHICH rounding a product uses is not written here: tools/gen_fp_schedule.py derives it with exact
@@ -48,8 +51,8 @@ __device__ __forceinline__ double fp_fold(double v, const FpC &c)
   const double k = __dadd_rn(__fma_rn(v, c.qinv, c.magic), -c.magic);
   return __fma_rn(-k, c.q, v);
 }
-/* t == w*y (mod q), exact integer.  COARSE = false: |y*winv| < 2^51, |t| <= q*(1/2 + |y|*2^-54);
- * COARSE = true: |y*winv| < 2^52, the quotient is rounded to an even integer, |t| <= q*(1 + |y|*2^-54).
+/* t == w*y (mod q), exact integer.  COARSE = false: |y*winv| < 2^51, |t| <= q*(1/2 + |y|*2^-55) for a centred table
+ * multiplier; COARSE = true: |y*winv| < 2^52, the quotient is rounded to an even integer, |t| <= q*(1 + |y|*2^-55).
  * Six FP64 instructions either way (tools/gen_fp_schedule.py decides which one a butterfly gets). */
 template <bool COARSE = false>
 __device__ __forceinline__ double fp_mul(double y, double w, double winv, const FpC &c)

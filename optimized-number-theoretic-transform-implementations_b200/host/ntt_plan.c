@@ -209,8 +209,11 @@ static int finish_inverse_constants(ntt_b200_plan_t *pl, uint64_t w_inv_1)
   pl->params.ninv     = make_mulc(pl->n_inv, pl->q, lazy);
   pl->params.ninv_w1  = make_mulc(nttm_mulmod(pl->n_inv % pl->q, w_inv_1 % pl->q, pl->q), pl->q, lazy);
   {
-    const double qd = (double)pl->q;
-    const double a = (double)(pl->n_inv % pl->q), b = (double)nttm_mulmod(pl->n_inv % pl->q, w_inv_1 % pl->q, pl->q);
+    /* FP64 path: multipliers centred to (-q/2, q/2) like the twiddle tables (k_build_fd) */
+    const double   qd = (double)pl->q;
+    const uint64_t ua = pl->n_inv % pl->q, ub = nttm_mulmod(pl->n_inv % pl->q, w_inv_1 % pl->q, pl->q);
+    const double   a = ua > (pl->q >> 1) ? -(double)(pl->q - ua) : (double)ua;
+    const double   b = ub > (pl->q >> 1) ? -(double)(pl->q - ub) : (double)ub;
     pl->params.ninv_fd[0]    = a;
     pl->params.ninv_fd[1]    = a / qd;
     pl->params.ninv_w1_fd[0] = b;

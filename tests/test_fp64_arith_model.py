@@ -40,13 +40,22 @@ def fp_fold(v, q):
     return fma(-k, qd, v)
 
 
+def centred(w, q):
+    """The table representative of a multiplier: w in (-q/2, q/2) (k_build_fd, finish_inverse_constants)."""
+    w %= q
+    return w - q if w > q // 2 else w
+
+
 def fp_mul(y, w, q, coarse=False):
+    """fp_mul of ntt_ring_fp.cuh with a TABLE multiplier: w is centred, winv = RN(w/q)."""
     qd = float(q)
-    winv = float(w) / qd
+    wc = float(centred(w, q))
+    winv = wc / qd
+    assert abs(winv) <= 0.5
     m = MAGIC2 if coarse else MAGIC
     cc = fma(y, winv, m) - m
-    h = y * float(w)
-    l = fma(y, float(w), -h)
+    h = y * wc
+    l = fma(y, wc, -h)
     d = fma(-cc, qd, h)
     return d + l, cc
 
@@ -55,47 +64,49 @@ def operands(q, limit_q, n, rng):
     """(y, w) pairs with |y| up to limit_q * q, biased to the extremes."""
     top = int(limit_q * q)
     for i in range(n):
-        w = rng.choice([1, 2, q - 1, q - 2, (q + 1) // 2, rng.randrange(1, q)])
+        w = rng.choice([1, 2, q - 1, q - 2, (q + 1) // 2, (q - 1) // 2, (q - 3) // 2, rng.randrange(1, q)])
         mag = rng.choice([top, top - 1, top - rng.randrange(1, 1 << 20), rng.randrange(0, top + 1), q, q - 1, 0])
         yield float(rng.choice([1, -1]) * mag), w
 
 
-@pytest.mark.parametrize("q,lim", [(Q49, 3.99), (Q50, 1.99)])
-def test_fp_mul_is_exact_below_2_pow_51(q, lim):
+@pytest.mark.parametrize("q,lim", [(Q49, 7.99), (Q50, 3.99)])
+def test_fp_mul_is_exact_below_2_pow_52(q, lim):
+    """Plain rounding with a centred multiplier: operands up to 2^52, |t| <= q*(1/2 + |y|*2^-55)."""
     rng = random.Random(1)
-    assert lim * q < (1 << 51)
+    assert lim * q < (1 << 52)
     for y, w in operands(q, lim, 4000, rng):
         t, cc = fp_mul(y, w, q)
         assert cc == int(cc) and t == int(t)
         assert (int(t) - int(y) * w) % q == 0
-        assert F(abs(int(t))) <= q * (F(1, 2) + F(abs(int(y)), 1 << 54))
+        assert F(abs(int(t))) <= q * (F(1, 2) + F(abs(int(y)), 1 << 55))
 
 
-def test_plain_rounding_breaks_beyond_2_pow_51_and_coarse_does_not():
-    """A negative operand whose quotient exceeds 2^51 lands where ulp = 1/2: the 1.5*2^52 constant yields a
-    half-integer quotient (the failure once seen on the GPU); the 3*2^52 constant stays exact up to 2^52."""
+def test_plain_rounding_breaks_beyond_2_pow_52_and_coarse_does_not():
+    """A negative quotient beyond 2^51 in magnitude lands where ulp = 1/2: the 1.5*2^52 constant yields a half-integer
+    quotient (the failure once seen on the GPU); the 3*2^52 constant stays exact up to 2^52.  With centred multipliers
+    (|w/q| <= 1/2) that takes an operand beyond 2^52."""
     q, rng = Q49, random.Random(2)
     broke = 0
     for _ in range(4000):
-        w = rng.randrange(q - (1 << 20), q)
-        y = -float(rng.randrange(int(4.2 * q), int(7.9 * q)))
+        w = (q - 1) // 2 - rng.randrange(0, 1 << 20)          # |w/q| close to 1/2, positive: y*w/q < -2^51
+        y = -float(rng.randrange(int(8.4 * q), int(15.9 * q)))
         _, cc = fp_mul(y, w, q)
         broke += cc != int(cc)
         t, ca = fp_mul(y, w, q, coarse=True)
         assert ca == int(ca) and int(ca) % 2 == 0 and t == int(t) and (int(t) - int(y) * w) % q == 0
-        assert F(abs(int(t))) <= q * (1 + F(abs(int(y)), 1 << 54))
+        assert F(abs(int(t))) <= q * (1 + F(abs(int(y)), 1 << 55))
     assert broke > 0
 
 
-@pytest.mark.parametrize("q,lim", [(Q49, 7.99), (Q50, 3.99)])
-def test_coarse_rounding_is_exact_below_2_pow_52(q, lim):
+@pytest.mark.parametrize("q,lim", [(Q49, 15.99), (Q50, 7.99)])
+def test_coarse_rounding_is_exact_below_2_pow_53(q, lim):
     rng = random.Random(3)
-    assert lim * q < (1 << 52)
+    assert lim * q < (1 << 53)
     for y, w in operands(q, lim, 4000, rng):
         t, ca = fp_mul(y, w, q, coarse=True)
         assert ca == int(ca) and int(ca) % 2 == 0 and t == int(t)
         assert (int(t) - int(y) * w) % q == 0
-        assert F(abs(int(t))) <= q * (1 + F(abs(int(y)), 1 << 54))
+        assert F(abs(int(t))) <= q * (1 + F(abs(int(y)), 1 << 55))
         assert abs(t) < (1 << 53)
 
 
@@ -137,11 +148,11 @@ def check_forward(passes, q):
                 assert b < P53
                 b = fb
             if p.coarse[s]:
-                assert b < P52
-                b = b + q * (1 + b / (1 << 54))
+                assert b < P53                               # |y*winv| <= |y|/2 < 2^52
+                b = b + q * (1 + b / (1 << 55))
             else:
-                assert b < P51
-                b = b + q * (F(1, 2) + b / (1 << 54))
+                assert b < P52                               # |y*winv| <= |y|/2 < 2^51
+                b = b + q * (F(1, 2) + b / (1 << 55))
             assert b < P53
         assert p.fold_end == 0
     return b
@@ -167,11 +178,11 @@ def check_inverse_pass(p, b_in, q, final):
             D = b[lo] + b[hi]
             assert D < P53                                   # X + Y and X - Y are exact
             if (p.coarse[s] >> lo) & 1:
-                assert D < P52 and not last
-                t = q * (1 + D / (1 << 54))
+                assert D < P53 and not last
+                t = q * (1 + D / (1 << 55))
             else:
-                assert D < P51
-                t = q * (F(1, 2) + D / (1 << 54))
+                assert D < P52
+                t = q * (F(1, 2) + D / (1 << 55))
             if last:
                 nb[lo] = nb[hi] = t
             else:
@@ -303,6 +314,46 @@ def test_inverse_networks_emulated_on_extreme_inputs(schedules, q50, q):
             big = max(out, key=abs) if not final else big
 
 
+@pytest.mark.parametrize("q50,q", [(0, Q49), (1, Q50)])
+def test_forward_network_emulated_on_extreme_inputs(schedules, q50, q):
+    """The L = 14 forward transform as the kernel runs it (passes A, B, C: 14 stages; with centred multipliers the first
+    schedule has NO fold before the final one), emulated with exact FMA on a pool of values that starts at the edges of
+    the centred input range [-2q, 2q): every stage pairs pool members with multipliers near +-q/2, and every value must
+    stay an integer, congruent to the exact butterfly, and inside the bound the schedule was derived from."""
+    rng = random.Random(11 + q50)
+    passes = schedules[("fwd", q50, 14)]
+    fb = F(q, 2) + 6
+    pool = [float(v) for v in (2 * q - 1, -2 * q, 2 * q - 2, -(2 * q - 1), q, -q, 1, 0)] + \
+           [float(rng.randrange(-2 * q, 2 * q)) for _ in range(24)]
+    exact = [int(v) for v in pool]
+    b = F(2 * q)
+    for p in passes:
+        n = 1 << p.R
+        for s in range(p.R):
+            fold, coarse = bool(p.fold_before[s]), bool(p.coarse[s])
+            assert p.fold_before[s] in (0, (1 << n) - 1) and p.coarse[s] in (0, (1 << n) - 1)
+            if fold:
+                pool = [fp_fold(v, q) for v in pool]
+                b = fb
+            b = b + (q * (1 + b / (1 << 55)) if coarse else q * (F(1, 2) + b / (1 << 55)))
+            order = sorted(range(len(pool)), key=lambda i: -abs(pool[i]))      # pair the largest with the largest
+            new, new_exact = list(pool), list(exact)
+            for a in range(0, len(order), 2):
+                i, j = order[a], order[a + 1]
+                w = rng.choice([(q - 1) // 2, (q + 1) // 2, (q - 1) // 2 - rng.randrange(1 << 20), rng.randrange(1, q)])
+                t, cc = fp_mul(pool[j], w, q, coarse=coarse)
+                assert cc == int(cc) and t == int(t)
+                new[i], new[j] = pool[i] + t, pool[i] - t
+                new_exact[i], new_exact[j] = exact[i] + exact[j] * w, exact[i] - exact[j] * w
+            pool, exact = new, new_exact
+            for v, e in zip(pool, exact):
+                assert v == int(v) and abs(v) < (1 << 53) and F(abs(int(v))) <= b and (int(v) - e) % q == 0
+    assert b < P53                                           # what the final fold accepts
+    for v, e in zip(pool, exact):
+        r = fp_fold(v, q)
+        assert r == int(r) and abs(r) <= q / 2 + 6 and (int(r) - e) % q == 0
+
+
 def primes_below(top, step, count):
     def is_prime(n):
         if n % 2 == 0:
@@ -333,8 +384,8 @@ def primes_below(top, step, count):
 @pytest.mark.parametrize("logn,top", [(13, (1 << 49) - 1024), (12, (1 << 50) - 2048), (14, (1 << 49) - 1024)])
 def test_final_stage_products_stay_below_q(logn, top):
     """The N^-1 stage converts its products without another fold, which needs |t| < q: the schedule keeps the
-    operands of that stage below 2^51 so the plain rounding applies (|t| <= q*(1/2 + 1/8)).  The worst multipliers
-    -- N^-1 * w_inv[1] close to q -- are tried on the largest moduli with operands at the top of that range."""
+    operands of that stage below 2^52 so the plain rounding applies (|t| <= q*(1/2 + 1/8)).  The actual multipliers
+    N^-1 and N^-1 * w_inv[1] (centred) are tried on the largest moduli with operands at the top of that range."""
     N, rng = 1 << logn, random.Random(6)
     worst = 0.0
     for q in primes_below(top, 2 * N, 40):
@@ -345,7 +396,7 @@ def test_final_stage_products_stay_below_q(logn, top):
         i = pow(x, (q - 1) // 4, q)             # a square root of -1: w_inv[1] is +-i
         for w in (ninv, ninv * i % q, ninv * (q - i) % q):
             for _ in range(300):
-                s = rng.choice([1, -1]) * ((1 << 51) - 1 - rng.choice([0, 1, rng.randrange(0, 1 << 30)]))
+                s = rng.choice([1, -1]) * ((1 << 52) - 1 - rng.choice([0, 1, rng.randrange(0, 1 << 30)]))
                 t, _ = fp_mul(float(s), w, q)
                 assert abs(t) < q and (int(t) - s * w) % q == 0
                 worst = max(worst, abs(t) / q)

@@ -8,20 +8,25 @@ sure the header on disk is the one this model produces.
     python tools/gen_fp_schedule.py --check    # exit 1 if the header is stale
 
 Arithmetic recap (see the header of ntt_ring_fp.cuh).  Coefficients are integers held in doubles, |v| < 2^53.
-For a twiddle w < q with winv = RN(w/q) (absolute error <= 2^-54) and an integer operand y:
-    plain   c = (y*winv + 1.5*2^52) - 1.5*2^52   one rounding to the nearest integer, needs |y*winv| < 2^51:
-            |t| <= q*(1/2 + |y|*2^-54)
-    coarse  c = (y*winv + 3*2^52) - 3*2^52       one rounding to the nearest EVEN integer, needs |y*winv| < 2^52:
-            |t| <= q*(1 + |y|*2^-54)
+Twiddles are stored CENTRED: w in (-q/2, q/2) with winv = RN(w/q), |winv| <= 1/2, absolute error <= 2^-55 (the doubles
+below 1/2 are 2^-54 apart).  For an integer operand y:
+    plain   c = (y*winv + 1.5*2^52) - 1.5*2^52   one rounding to the nearest integer, needs |y*winv| < 2^51, i.e.
+            |y| < 2^52:  |t| <= q*(1/2 + |y|*2^-55)
+    coarse  c = (y*winv + 3*2^52) - 3*2^52       one rounding to the nearest EVEN integer, needs |y*winv| < 2^52, i.e.
+            |y| < 2^53:  |t| <= q*(1 + |y|*2^-55)
 both followed by the same exact h/l/d/t steps (6 FP64 instructions either way).  A fold is v - rint(v/q)*q,
 |result| <= q/2 + 6 for |v| < 2^53 (3 instructions).
+(Until the centred tables, w lay in [0,q): the operand limits were 2^51 / 2^52 and the error term |y|*2^-54, which cost
+the N = 2^14 forward transform a fold of every value after its eighth stage; centred, fourteen stages fit under 2^53
+without one.)
 
 Forward (Cooley-Tukey, X' = X + t, Y' = X - t): every value of a stage has the same bound b' = b + |t|(b), so the
-schedule is per stage: plain while b < 2^51, coarse while b < 2^52, else fold everything first.
+schedule is per stage: plain while b < 2^52, coarse above, and a fold of everything first whenever the new bound would
+reach 2^53.
 Inverse (Gentleman-Sande, X' = X + Y, Y' = t(X - Y)): sums double but products come back small, so bounds depend
 on the POSITION inside the register network -- only a few of the 2^R values ever get large.  The schedule tracks
-one bound per position and folds exactly the positions that would break a limit (operand of a product < 2^52,
-sums < 2^53), plus the positions above a cap at the end of a pass so the next pass (whose threads regroup the
+one bound per position and folds exactly the positions that would break a limit (sums and product operands < 2^53,
+< 2^52 where the rounding must be plain), plus the positions above a cap at the end of a pass so the next pass (whose threads regroup the
 values) can start from one uniform bound.  The caps are searched for the fewest folds.
 """
 import os
@@ -41,14 +46,14 @@ def fold_bound(q):
 
 def t_plain(y, q):
     if isinstance(y, float):                              # cap search: floats are enough to rank candidates
-        return q * (0.5 + y / 18014398509481984.0)
-    return q * (F(1, 2) + y / (1 << 54))
+        return q * (0.5 + y / 36028797018963968.0)
+    return q * (F(1, 2) + y / (1 << 55))
 
 
 def t_coarse(y, q):
     if isinstance(y, float):
-        return q * (1.0 + y / 18014398509481984.0)
-    return q * (1 + y / (1 << 54))
+        return q * (1.0 + y / 36028797018963968.0)
+    return q * (1 + y / (1 << 55))
 
 
 class Pass:
@@ -76,17 +81,24 @@ def forward_schedule(L, q50):
     for p in passes:
         n = 1 << p.R
         for s in range(p.R):
-            if b >= P52 or (b >= P51 and b + t_coarse(b, q) >= P53):
-                p.fold_before[s] = (1 << n) - 1
-                b = fold_bound(q)
-            if b < P51:
-                b = b + t_plain(b, q)
-            else:
-                p.coarse[s] = (1 << n) - 1
-                b = b + t_coarse(b, q)
-            assert b < P53
+            b = forward_stage(p, s, n, b, q)
         p.b_out = b
     return passes
+
+
+def forward_stage(p, s, n, b, q):
+    """One forward stage on the uniform bound b: plain rounding while the operand is below 2^52, coarse above; everything
+    is folded first if the operand or the new bound would reach 2^53.  Returns the new bound."""
+    def step(v):
+        return (v + t_plain(v, q), False) if v < P52 else (v + t_coarse(v, q), True)
+    nb, coarse = step(b)
+    if b >= P53 or nb >= P53:
+        p.fold_before[s] = (1 << n) - 1
+        nb, coarse = step(fold_bound(q))
+    if coarse:
+        p.coarse[s] = (1 << n) - 1
+    assert nb < P53
+    return nb
 
 
 def inverse_pass(R, b_in, q, final, cap_out, paired=False):
@@ -104,7 +116,7 @@ def inverse_pass(R, b_in, q, final, cap_out, paired=False):
     for s in range(R):
         d = 1 << s
         last = final and s == R - 1
-        lim = P51 if last else P52
+        lim = P52 if last else P53                      # operand of a plain / coarse product
         joint = paired and s >= 1
         for lo in range(n):
             if lo & d or (joint and lo & 1):
@@ -122,7 +134,7 @@ def inverse_pass(R, b_in, q, final, cap_out, paired=False):
             if lo & d or (joint and lo & 1):
                 continue
             los = (lo, lo + 1) if joint else (lo,)
-            coarse = any(b[l] + b[l + d] >= P51 for l in los)
+            coarse = any(b[l] + b[l + d] >= P52 for l in los)
             for l in los:
                 D = b[l] + b[l + d]
                 if coarse:
@@ -218,15 +230,7 @@ def forward_pass_schedule(R, q50):
     n = 1 << R
     b = F(2 * q)
     for s in range(R):
-        if b >= P52 or (b >= P51 and b + t_coarse(b, q) >= P53):
-            p.fold_before[s] = (1 << n) - 1
-            b = fold_bound(q)
-        if b < P51:
-            b = b + t_plain(b, q)
-        else:
-            p.coarse[s] = (1 << n) - 1
-            b = b + t_coarse(b, q)
-        assert b < P53
+        b = forward_stage(p, s, n, b, q)
     p.b_out = b
     return p
 
