@@ -655,8 +655,17 @@ static int host_apply(const ntt_b200_plan_t *plan, uint64_t *h_a, size_t batch, 
   const size_t poly_words = (size_t)pl->N;
   size_t       done = 0;
   int          slot = 0;
+  size_t       ramp = pl->pipe_polys >> 3; /* first chunk: an eighth of a full one */
+  if(ramp < 1) ramp = 1;
   while(!rc && done < batch) {
-    const size_t take  = batch - done < pl->pipe_polys ? batch - done : pl->pipe_polys;
+    /* Chunk sizes ramp up 1/8, 1/4, 1/2, 1 at the head and halve again over the tail: the first H2D copy has no D2H to
+     * overlap with and the last D2H copy no H2D, so both should be short (with equal chunks of 32 MiB the two
+     * unpaired copies cost 1/16 of a 512 MiB batch each). */
+    const size_t left = batch - done;
+    size_t       take = ramp < pl->pipe_polys ? ramp : pl->pipe_polys;
+    if(left <= 2 * take && left > 2 * (pl->pipe_polys >> 3) + 1) take = (left + 1) / 2;
+    if(take > left) take = left;
+    if(ramp < pl->pipe_polys) ramp <<= 1; /* (stops doubling at the full size: it must never wrap to 0) */
     const size_t bytes = take * poly_words * 8;
     void *       st    = pl->pipe_stream[slot];
     uint64_t *   d     = pl->pipe_buf[slot];

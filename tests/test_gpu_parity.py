@@ -450,6 +450,33 @@ def test_host_batch_api_pinned_and_pageable(ntt, oracle, golden_synth):
     plan.close()
 
 
+def test_host_pipeline_many_chunks(ntt, oracle, golden_synth, monkeypatch):
+    """The host-buffer pipeline with far more than 64 chunks (1 MiB chunks, 80 MiB batch; chunk sizes ramp up at the head
+    and halve over the tail): every row equals the device-resident result, ragged batch sizes included."""
+    import os
+    s = [x for x in golden_synth if x["m"] == 13][0]
+    N, q = 1 << 13, s["q"]
+    monkeypatch.setenv("NTT_B200_PIPE_MIB", "1")               # 16 polynomials of 64 KiB per chunk
+    try:
+        plan = ntt.Plan.from_psi(N, q, s["psi"])
+        for batch in (1283, 1, 17, 32, 33):
+            a = oracle.uniform(batch * N, q, 43 + batch).reshape(batch, N)
+            h = a.copy()
+            plan.fwd_host(h, batch)
+            d = to_dev(a)
+            plan.fwd(d, batch)
+            assert np.array_equal(h, to_host(d).reshape(batch, N)), batch
+            plan.inv_host(h, batch)
+            assert np.array_equal(h, a), batch
+        plan.close()
+    finally:
+        os.environ["NTT_B200_PIPE_MIB"] = "32"                 # the setting is process-wide: put the default back
+        p2 = ntt.Plan.from_psi(N, q, s["psi"])
+        x = oracle.uniform(N, q, 5).reshape(1, N)
+        p2.fwd_host(x, 1)
+        p2.close()
+
+
 def test_large_n_two_pass_split(ntt, oracle):
     """N = 2^20 (strided passes + chunk kernel): one polynomial against the oracle."""
     m, q = 20, 0x1FFFFFC800001
