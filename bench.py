@@ -484,7 +484,9 @@ def run_config5(ntt, torch, dist, rank, world, local):
 
     # the same exchange with a BATCH of transforms per launch / barrier: the single transform is latency-bound
     # (32 MB over 8 GPUs), a batch amortises the launches and the barrier and fills the SMs
-    B = 8
+    # 9 transforms = 288 chunks of 2^14 per rank at 8 ranks: two full waves of the 148 persistent CTAs (8 would leave a
+    # quarter of the second wave empty)
+    B = 9
     ab = np.stack([a] + [splitmix64_mod(N, q, 40 + i) for i in range(1, B)])
     fb = fs.FusedDistributedNtt(N, q, psi, rank, world, local, dist, batch=B)
     fb.px.load_slice(np.ascontiguousarray(ab[:, rank::world]).reshape(-1))
