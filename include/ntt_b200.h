@@ -50,6 +50,10 @@ const char *ntt_b200_version(void);
  *   "fp64" 0/1  run the ring kernel's butterflies on the FP64 pipe when q <= 2^50-2048 (default 1)
  *   "polymul" 0/1  one-kernel negacyclic multiply at N = 2^13 (default 1; 0 = compose it from transforms)
  * The same switches are read from NTT_B200_NO_RING=1 / NTT_B200_NO_FP64=1 / NTT_B200_NO_FUSED_POLYMUL=1 at first use.
+ * Further environment switches, read once: NTT_B200_NO_FP_STRIDED=1 (N >= 2^15 in the FP64 range: integer instead of FP64
+ * strided passes), NTT_B200_NO_RNS_MULTI=1 (RNS batches: one launch per limb instead of one per kernel),
+ * NTT_B200_PIPE_MIB / NTT_B200_PIPE_DEPTH (host-buffer pipeline: chunk size in MiB, default 32, and chunks in flight,
+ * default 4).
  */
 int ntt_b200_configure(const char *key, int value);
 
