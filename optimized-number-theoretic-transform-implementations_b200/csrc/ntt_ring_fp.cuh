@@ -318,9 +318,8 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
   };
   const size_t   my_blocks = my_polys * NB;
   const size_t   groups    = (size_t)1 << (p0.logn - 4);
-  /* single plan: the constants of the transform are loop invariants (kept out of the loop by hand: hoisting them
-   * from inside changed the schedule of the headline kernel by half a percent) */
-  /* the plan of this CTA: the kernel's own (single plan), or its limb's entry of the argument table */
+  /* The plan of this CTA: the kernel's own (single plan), or its limb's entry of the argument table.  Its constants
+   * are loop invariants and are set up here, outside the loop over the chunks. */
   const ntt_cuda_params_t &p = ring_plan_of<MULTI>(p0, limbs, my_limb);
   /* q and 1/q feed one operand of 288 of the forward kernel's 801 DFMAs.  Read as limbs.e[my_limb].q_fd they come out
    * of an indexed constant-bank load into ORDINARY registers and those DFMAs pay for a third register operand (3.2
