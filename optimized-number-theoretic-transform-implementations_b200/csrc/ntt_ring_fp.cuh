@@ -116,8 +116,8 @@ template <int KIND, bool Q50, int L, int WHICH>
 struct FpSel {
   static __host__ __device__ constexpr FpPass get()
   {
-    const FpSchedule &s = KIND == 0 ? FP_SCHED_FWD[Q50][L - 12]
-                                    : (KIND == 1 ? FP_SCHED_INV[Q50][L - 12] : FP_SCHED_INV_NOFINAL[Q50][L - 12]);
+    const FpSchedule &s = KIND == 0 ? FP_SCHED_FWD[Q50][L - 11]
+                                    : (KIND == 1 ? FP_SCHED_INV[Q50][L - 11] : FP_SCHED_INV_NOFINAL[Q50][L - 11]);
     return WHICH == 0 ? s.a : (WHICH == 1 ? s.b : s.c);
   }
 };
