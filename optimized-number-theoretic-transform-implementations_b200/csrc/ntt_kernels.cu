@@ -813,8 +813,8 @@ static int try_ring(int device, int L, const ntt_cuda_params_t &p, uint64_t *d_a
                     bool *done, const RingOpts *o = nullptr)
 {
   *done = false;
-  if(!ring_enabled() || !p.lazy || L < 11 || L > 14) return 0;
-  if(L == 11 && !use_fp64(p, FWD)) return 0; /* chunks of 2^11: FP64 ring kernel only */
+  if(!ring_enabled() || !p.lazy || L < 10 || L > 14) return 0;
+  if(L <= 11 && !use_fp64(p, FWD)) return 0; /* chunks of 2^10 / 2^11: FP64 ring kernel only */
   if(!(FWD ? p.fwd_ct_wu : p.inv_ct_wu)) return 0;
   if(((uintptr_t)d_a & 127) != 0) return 0; /* TMA wants 128-byte aligned rows (cudaMalloc gives 256) */
   if(o && o->d_other && !use_fp64(p, FWD)) return 0; /* the fused product exists on the FP64 kernel only */
@@ -823,6 +823,7 @@ static int try_ring(int device, int L, const ntt_cuda_params_t &p, uint64_t *d_a
     const RingOpts none;
     const RingOpts &ro = o ? *o : none;
     switch(L) {
+      case 10: return ring_fp_launch_10(FWD, device, p, d_a, n_chunks, st, ro);
       case 11: return ring_fp_launch_11(FWD, device, p, d_a, n_chunks, st, ro);
       case 12: return ring_fp_launch_12(FWD, device, p, d_a, n_chunks, st, ro);
       case 13: return ring_fp_launch_13(FWD, device, p, d_a, n_chunks, st, ro);
@@ -1145,7 +1146,7 @@ extern "C" int ntt_cuda_describe(const ntt_cuda_params_t *p, int inverse, char *
   const Split sp  = make_split((int)p->logn);
   const bool  fwd = !inverse;
   char        chunk[64];
-  const bool  ring = ring_enabled() && p->lazy && sp.L <= 14 && (sp.L >= 12 || (sp.L == 11 && use_fp64(*p, fwd))) &&
+  const bool  ring = ring_enabled() && p->lazy && sp.L <= 14 && (sp.L >= 12 || (sp.L >= 10 && use_fp64(*p, fwd))) &&
                     (fwd ? p->fwd_ct_wu : p->inv_ct_wu);
   if(ring && use_fp64(*p, fwd)) snprintf(chunk, sizeof(chunk), "k_ring_fp<%d,%s>", sp.L, fwd ? "fwd" : "inv");
   else if(ring) snprintf(chunk, sizeof(chunk), "k_ring<%d,%s>", sp.L, fwd ? "fwd" : "inv");

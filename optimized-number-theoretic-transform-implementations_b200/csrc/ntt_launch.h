@@ -48,6 +48,8 @@ struct RingOpts {
 };
 
 /* one launcher per translation unit; `fwd` selects the direction */
+int ring_fp_launch_10(bool fwd, int device, const ntt_cuda_params_t &p, uint64_t *d_a, size_t n_chunks, cudaStream_t st,
+                      const RingOpts &o);
 int ring_fp_launch_11(bool fwd, int device, const ntt_cuda_params_t &p, uint64_t *d_a, size_t n_chunks, cudaStream_t st,
                       const RingOpts &o);
 int ring_fp_launch_12(bool fwd, int device, const ntt_cuda_params_t &p, uint64_t *d_a, size_t n_chunks, cudaStream_t st,

@@ -1,7 +1,7 @@
 /*
  * csrc/ntt_ring.cuh -- the headline kernel: persistent CTAs, TMA slot ring, three register-tiled passes.
  *
- * A chunk of 2^L coefficients (L = 11 .. 14; a whole polynomial when N = 2^L) is NB = 2^(L-9) "blocks"
+ * A chunk of 2^L coefficients (L = 10 .. 14; a whole polynomial when N = 2^L) is NB = 2^(L-9) "blocks"
  * of 512 coefficients (4 KiB).  Shared memory is a ring of SLOTS 4-KiB slots; block g of the CTA's work
  * sequence lives in slot g mod SLOTS.  Blocks arrive by TMA (cp.async.bulk.tensor, SWIZZLE_128B, one
  * mbarrier per polynomial-in-flight), results leave by TMA store straight out of the slot, and the slot is
@@ -165,14 +165,15 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *tm)
 
 template <int L>
 struct RingCfg {
-  static_assert(L >= 11 && L <= 14, "ring kernel covers chunks of 2^11 .. 2^14");
+  static_assert(L >= 10 && L <= 14, "ring kernel covers chunks of 2^10 .. 2^14");
   static constexpr int RA       = L - 9;                  /* stages of pass A */
   static constexpr int NB       = 1 << RA;                /* 512-element blocks per chunk */
   static constexpr int WARPS    = NB / 2;
   static constexpr int THREADS  = WARPS * 32;
-  /* resident CTAs per SM: 16 warps per SM, except at L = 11 (two warps per CTA), where eight CTAs would leave each
-   * of them less shared memory than a ring deeper than one polynomial needs: six CTAs with eight slots each */
-  static constexpr int CTAS     = L == 11 ? 6 : 512 / THREADS;
+  /* resident CTAs per SM: 16 warps per SM, except at L = 11 / 10 (two warps / one warp per CTA), where that many CTAs
+   * would leave each of them less shared memory than a ring deeper than one polynomial needs: six CTAs with eight slots
+   * each at L = 11, twelve CTAs with three slots each at L = 10 */
+  static constexpr int CTAS     = L == 11 ? 6 : (L == 10 ? 12 : 512 / THREADS);
   static constexpr int NBAR     = 4;                      /* polynomials in flight (mbarrier ring) */
   /* shared-memory copy of the twiddles of passes A and B: NB-1 entries for pass A, 31 per block for pass B */
   static constexpr int NTW      = NB - 1 + NB * 31;
@@ -180,10 +181,11 @@ struct RingCfg {
   /* 228 KiB per SM, 1 KiB reserved per resident CTA, at most 227 KiB per CTA */
   static constexpr int PER_CTA  = 233472 / CTAS - 1024;
   static constexpr int BUDGET   = PER_CTA < 232448 ? PER_CTA : 232448;
-  /* the inverse re-arms a dead polynomial with four big TMA boxes of BOXB = NB/4 adjacent blocks each
-   * (BOXB*32 rows <= 256): the ring depth is a multiple of BOXB so that a box never wraps */
-  static constexpr int BOXB     = NB / 4;
-  static constexpr int SLOTS    = ((BUDGET - TW_BYTES - 1024 - 128) / 4096) / (NB / 2) * (NB / 2); /* 48 / 24 / 12 / 8 for L = 14 / 13 / 12 / 11 */
+  /* the inverse re-arms a dead polynomial with NBOX = 4 big TMA boxes of BOXB = NB/4 adjacent blocks each (two boxes of
+   * one block at L = 10; BOXB*32 rows <= 256): the ring depth is a multiple of BOXB so that a box never wraps */
+  static constexpr int BOXB     = NB >= 4 ? NB / 4 : 1;
+  static constexpr int NBOX     = NB / BOXB;
+  static constexpr int SLOTS    = ((BUDGET - TW_BYTES - 1024 - 128) / 4096) / (NB / 2) * (NB / 2); /* 48 / 24 / 12 / 8 / 3 for L = 14 / 13 / 12 / 11 / 10 */
   static constexpr int SMEM     = SLOTS * 4096 + 1024 /* alignment slack */ + TW_BYTES + 128 /* 8 load barriers + the CTA barrier */;
   /* FP64 kernel: 16-byte twiddle entries; at L = 14 the cache also holds the FIRST-stage twiddle of pass C for every
    * 16-coefficient group (NB*32 entries), so that the last pass starts from shared memory while its other 14

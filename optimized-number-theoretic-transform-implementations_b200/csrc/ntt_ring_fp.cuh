@@ -116,8 +116,8 @@ template <int KIND, bool Q50, int L, int WHICH>
 struct FpSel {
   static __host__ __device__ constexpr FpPass get()
   {
-    const FpSchedule &s = KIND == 0 ? FP_SCHED_FWD[Q50][L - 11]
-                                    : (KIND == 1 ? FP_SCHED_INV[Q50][L - 11] : FP_SCHED_INV_NOFINAL[Q50][L - 11]);
+    const FpSchedule &s = KIND == 0 ? FP_SCHED_FWD[Q50][L - 10]
+                                    : (KIND == 1 ? FP_SCHED_INV[Q50][L - 10] : FP_SCHED_INV_NOFINAL[Q50][L - 10]);
     return WHICH == 0 ? s.a : (WHICH == 1 ? s.b : s.c);
   }
 };
@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
     tma_prefetch_desc(&tmap);
     tma_prefetch_desc(&tmap2);
     /* forward: one arrival per block; inverse: one per box, two boxes per half */
-    for(int i = 0; i < 2 * C::NBAR; i++) mbar_init(bars + 8u * i, FWD ? HALF : 2);
+    for(int i = 0; i < 2 * C::NBAR; i++) mbar_init(bars + 8u * i, FWD ? HALF : C::NBOX / 2);
     mbar_init(cta_bar, C::WARPS); /* the inverse's block-wide barrier: one arrival per warp (see below) */
     fence_barrier_init();
   }
@@ -472,7 +472,7 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
        * barrier, the other warps only arrive and go straight on to their butterflies) and re-arms the ring */
       if(warp == 0) {
         named_sync(T);
-        if(lane < 4) issue_box(g0 + C::BOXB * lane + SLOTS);
+        if(lane < (uint32_t)C::NBOX) issue_box(g0 + C::BOXB * lane + SLOTS);
         __syncwarp();
       } else {
         named_arrive(T);

@@ -112,9 +112,9 @@ static void fill_params(ntt_b200_plan_t *pl)
   p->lazy      = nttm_bitlen(pl->q) <= LAZY_MAX_QBITS ? 1u : 0u;
   p->red_shift = nttm_bitlen(pl->q) > 9 ? nttm_bitlen(pl->q) - 9 : 0;
   p->red_mu    = (uint32_t)((((u128)1) << (32 + p->red_shift)) / pl->q);
-  /* FP64 ring kernel: q <= 2^50 - 2048 and a chunk size the ring kernel serves (N >= 2^11) */
+  /* FP64 ring kernel: q <= 2^50 - 2048 and a chunk size the ring kernel serves (N >= 2^10) */
   p->fp64 = 0;
-  if(pl->logn >= 11) {
+  if(pl->logn >= 10) {
     if(pl->q <= ((uint64_t)1 << 49) - 1024) p->fp64 = 1;
     else if(pl->q <= ((uint64_t)1 << 50) - 2048) p->fp64 = 2;
   }
@@ -164,10 +164,10 @@ static int build_direction(ntt_b200_plan_t *pl, const uint64_t *d_w, void **wu, 
   return NTT_B200_SUCCESS;
 }
 
-/* pass-C copies of the last four stages (lazy path, N >= 2^11: the sizes the ring kernels serve) */
+/* pass-C copies of the last four stages (lazy path, N >= 2^10: the sizes the ring kernels serve) */
 static int build_ctables(ntt_b200_plan_t *pl, const void *wu, const void *qq, void **ct_wu, void **ct_qq)
 {
-  if(!pl->params.lazy || pl->logn < 11) return NTT_B200_SUCCESS;
+  if(!pl->params.lazy || pl->logn < 10) return NTT_B200_SUCCESS;
   const size_t entries = (size_t)15 << (pl->logn - 4);
   if(ntt_cuda_malloc(pl->device, ct_wu, entries * 16) || ntt_cuda_malloc(pl->device, ct_qq, entries * 8))
     return cuda_error("table alloc");

@@ -197,7 +197,7 @@ def check_inverse_pass(p, b_in, q, final):
 @pytest.mark.parametrize("q50,q", [(0, (1 << 49) - 1025), (0, Q49), (0, 0x1fffffc800001), (0, 7681),
                                    (1, (1 << 50) - 2049), (1, 0x3ffffffef4001), (1, (1 << 49) - 1023)])
 def test_schedules_stay_inside_their_limits(schedules, q50, q):
-    for L in (11, 12, 13, 14):
+    for L in (10, 11, 12, 13, 14):
         b = check_forward(schedules[("fwd", q50, L)], q)
         assert b < P53                                       # what the final fold accepts
         pc, pb, pa = schedules[("inv", q50, L)]

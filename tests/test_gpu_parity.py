@@ -271,12 +271,12 @@ def test_headline_config_roundtrip_and_linearity(ntt, oracle, golden_synth):
 
 
 @pytest.mark.parametrize("m,bits", [(14, 49), (14, 50), (13, 49), (13, 50), (12, 49), (12, 50), (11, 49), (11, 50),
-                                    (16, 49), (16, 50)])
+                                    (10, 49), (10, 50),                                     (16, 49), (16, 50)])
 def test_kernel_paths_agree_on_full_batch(ntt, oracle, golden_synth, m, bits):
     """The three CUDA paths (FP64 ring, integer ring, generic smem kernel) must produce identical bytes on a
     large batch, forward and inverse, on inputs at the edge of the contracts; rows are spot-checked vs the oracle.
     bits = 49: the headline modulus (first FP64 range schedule); 50: the largest 50-bit prime (second schedule).
-    m = 11 .. 14: the four ring-kernel geometries (11: FP64 ring kernel only); 16: strided pass + 2^14 chunks."""
+    m = 10 .. 14: the five ring-kernel geometries (10, 11: FP64 ring kernel only); 16: strided pass + 2^14 chunks."""
     N = 1 << m
     batch = (1 << 25) >> m  # 2^25 coefficients per direction: 2048 polynomials at N = 2^14
     if bits == 49:

@@ -8,7 +8,7 @@ PKG=$ROOT/optimized-number-theoretic-transform-implementations_b200
 name=$1; shift
 OUT=$ROOT/build_exp; mkdir -p $OUT/obj_$name
 NV="nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -DNTT_EXPERIMENT $*"
-for f in ntt_ring_fp_11 ntt_ring_fp_12 ntt_ring_fp_13 ntt_ring_fp_14; do
+for f in ntt_ring_fp_10 ntt_ring_fp_11 ntt_ring_fp_12 ntt_ring_fp_13 ntt_ring_fp_14; do
   $NV -c $PKG/csrc/$f.cu -o $OUT/obj_$name/$f.o &
 done
 wait

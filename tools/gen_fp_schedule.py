@@ -262,7 +262,7 @@ def all_schedules():
     for q50 in (0, 1):
         out[("pminv", q50, 13)] = list(polymul_inverse_schedule(q50))
     for q50 in (0, 1):
-        for L in (11, 12, 13, 14):
+        for L in (10, 11, 12, 13, 14):
             out[("fwd", q50, L)] = forward_schedule(L, q50)
             pc, pb, pa, pn = inverse_schedule(L, q50)
             out[("inv", q50, L)] = [pc, pb, pa]
@@ -277,7 +277,7 @@ def render():
         " * Range schedules of the FP64 ring kernels: which positions of a register network are folded before each",
         " * stage (processing order), which butterflies use the coarse quotient rounding, which positions are folded",
         " * after the last stage.  Bit i = position i (for `coarse`: the butterfly whose lower position is i).",
-        " * Indexed [Q50][L-11]; passes A, B, C as in ntt_ring_fp.cuh.  tests/test_fp64_arith_model.py re-derives",
+        " * Indexed [Q50][L-10]; passes A, B, C as in ntt_ring_fp.cuh.  tests/test_fp64_arith_model.py re-derives",
         " * every bound with exact rationals and fails if this file is stale. */",
         "#pragma once",
         "#include <cstdint>",
@@ -299,10 +299,10 @@ def render():
                                      "0x%08xu" % p.fold_end)
 
     for kind, name in (("fwd", "FP_SCHED_FWD"), ("inv", "FP_SCHED_INV"), ("invnf", "FP_SCHED_INV_NOFINAL")):
-        lines.append("constexpr FpSchedule %s[2][4] = {" % name)
+        lines.append("constexpr FpSchedule %s[2][5] = {" % name)
         for q50 in (0, 1):
             lines.append("  {")
-            for L in (11, 12, 13, 14):
+            for L in (10, 11, 12, 13, 14):
                 ps = sch[(kind, q50, L)]
                 if kind == "fwd":
                     a, b, c = ps
