@@ -46,7 +46,7 @@ int ntt_b200_device_count(void);
 const char *ntt_b200_version(void);
 /*
  * Kernel selection, for benchmarks and A/B parity tests only (every choice is a CUDA path):
- *   "ring" 0/1  persistent TMA ring kernel for chunks of 2^12..2^14 (default 1; 0 = generic smem kernel)
+ *   "ring" 0/1  persistent TMA ring kernel for chunks of 2^10..2^14 (2^10, 2^11: FP64 range only; default 1; 0 = generic smem kernel)
  *   "fp64" 0/1  run the ring kernel's butterflies on the FP64 pipe when q <= 2^50-2048 (default 1)
  *   "polymul" 0/1  one-kernel negacyclic multiply at N = 2^13 (default 1; 0 = compose it from transforms)
  * The same switches are read from NTT_B200_NO_RING=1 / NTT_B200_NO_FP64=1 / NTT_B200_NO_FUSED_POLYMUL=1 at first use.

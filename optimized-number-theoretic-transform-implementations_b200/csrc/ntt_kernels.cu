@@ -805,7 +805,7 @@ namespace nttb200 {
 size_t nl_min_chunks_per_cta() { return g_min_chunks_per_cta; }
 }  // namespace nttb200
 
-/* true if the ring kernel handled the chunk stage (lazy path, chunk of 2^12..2^14, pass-C tables present).
+/* true if the ring kernel handled the chunk stage (lazy path, chunk of 2^10..2^14 -- 2^10 and 2^11 on the FP64 kernel only --, pass-C tables present).
  * `o` (forward only): fused pointwise product / lazy output, honoured by the FP64 kernel only -- if they are asked
  * for and the FP64 kernel cannot run, nothing is launched and *done stays false. */
 template <bool FWD>
