@@ -354,6 +354,41 @@ def test_forward_network_emulated_on_extreme_inputs(schedules, q50, q):
         assert r == int(r) and abs(r) <= q / 2 + 6 and (int(r) - e) % q == 0
 
 
+@pytest.mark.parametrize("q50,q", [(0, Q49), (1, Q50)])
+def test_strided_inverse_networks_emulated_on_extreme_inputs(schedules, q50, q):
+    """k_strided_fp inverse passes (R = 1..5, with and without the N^-1 stage), emulated with exact FMA on inputs pinned
+    to the edges of the centred input range [-q, q): integers below 2^53 throughout, congruent to the exact
+    Gentleman-Sande network, and below q in magnitude after the N^-1 stage (converted without a fold)."""
+    rng = random.Random(21 + q50)
+    ninv, ninv_w = rng.randrange(1, q), rng.randrange(1, q)
+    for R in range(1, 6):
+        n = 1 << R
+        for kind, final in (("sinv", True), ("sinvnf", False)):
+            (p,) = schedules[(kind, q50, R)]
+            for trial in range(25):
+                edge = rng.choice([q, -q, q - 1, 1 - q, None])
+                x = [float(edge if edge is not None else rng.randrange(-q, q)) for _ in range(n)]
+                ex = [int(v) for v in x]
+                tw = {(u, sub): rng.choice([1, q - 1, (q - 1) // 2, (q + 1) // 2, rng.randrange(1, q)])
+                      for u in range(R) for sub in range(1 << u)}
+                out = emulate_inverse_pass(p, list(x), tw, q, final, ninv, ninv_w)
+                for s_ in range(R):
+                    u, d = R - 1 - s_, 1 << s_
+                    if final and u == 0:
+                        for k in range(d):
+                            a, b = ex[k], ex[k + d]
+                            ex[k], ex[k + d] = (a + b) * ninv, (a - b) * ninv_w
+                    else:
+                        for sub in range(1 << u):
+                            for k in range(d):
+                                lo = sub * 2 * d + k
+                                a, b = ex[lo], ex[lo + d]
+                                ex[lo], ex[lo + d] = a + b, (a - b) * tw[(u, sub)]
+                for got, want in zip(out, ex):
+                    assert got == int(got) and (int(got) - want) % q == 0
+                    assert abs(got) < (q if final else (1 << 53))
+
+
 def primes_below(top, step, count):
     def is_prime(n):
         if n % 2 == 0:
