@@ -309,13 +309,26 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
     cta_in_limb = blockIdx.x;
   }
   const uint32_t limb_chunks = ppl << s1; /* MULTI: chunks of one limb */
-  const size_t   my_polys  = MULTI ? (limb_chunks > cta_in_limb ? (limb_chunks - cta_in_limb + cpl - 1) / cpl : 0)
-                                   : ((n_chunks > blockIdx.x) ? (n_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0);
+  size_t my_polys = MULTI ? (limb_chunks > cta_in_limb ? (limb_chunks - cta_in_limb + cpl - 1) / cpl : 0)
+                          : ((n_chunks > blockIdx.x) ? (n_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0);
+  /* single plan, chunks of a LARGER transform (s1 > 0): the work sequence is ordered (chunk-in-polynomial, polynomial)
+   * and every CTA takes a CONTIGUOUS range of it, so that it keeps its chunk-in-polynomial -- and with it the 48 KiB
+   * twiddle cache -- for as long as possible; in plain chunk order (every gridDim-th chunk) it changed on every chunk
+   * from N = 2^17 on (148 CTAs, 2^s1 chunks per polynomial) and the refill cost 15 % of the kernel.  Batches of 2^31
+   * chunks or more keep the plain order. */
+  const uint32_t n_polys32 = (uint32_t)(n_chunks >> s1);
+  const bool     cp_major  = !MULTI && s1 != 0 && n_chunks < ((size_t)1 << 31);
+  const size_t   range_lo  = cp_major ? (size_t)blockIdx.x * n_chunks / gridDim.x : 0;
   auto chunk_of = [&](size_t k) -> size_t {
-    if(!MULTI) return blockIdx.x + k * gridDim.x;
+    if(!MULTI) {
+      if(!cp_major) return blockIdx.x + k * gridDim.x;
+      const uint32_t i = (uint32_t)(range_lo + k), cpv = i / n_polys32, rest = i - cpv * n_polys32;
+      return ((size_t)rest << s1) + cpv;
+    }
     const uint32_t i = cta_in_limb + (uint32_t)k * cpl, cpv = i / ppl, rest = i - cpv * ppl;
     return ((size_t)(my_limb * ppl + rest) << s1) + cpv;
   };
+  if(cp_major) my_polys = (size_t)(blockIdx.x + 1) * n_chunks / gridDim.x - range_lo;
   const size_t   my_blocks = my_polys * NB;
   const size_t   groups    = (size_t)1 << (p0.logn - 4);
   /* The plan of this CTA: the kernel's own (single plan), or its limb's entry of the argument table.  Its constants
@@ -389,7 +402,7 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
   bool     c1_done   = false; /* inverse: this warp already ran pass C on the first block of polynomial k */
   uint32_t sl_next = 0; /* slot of block 0 of the next polynomial: (k * NB) mod SLOTS, kept in 32 bits */
   for(size_t k = 0; k < my_polys; k++) {
-    const size_t   chunk = MULTI ? chunk_of(k) : blockIdx.x + k * gridDim.x;
+    const size_t   chunk = chunk_of(k);
     const uint32_t cp    = (uint32_t)(chunk & (((size_t)1 << s1) - 1));
     const uint32_t cache_key = cp;
     if(cache_key != cached_cp) {
@@ -627,7 +640,7 @@ __global__ void __launch_bounds__(RingCfg<L>::THREADS, RingCfg<L>::CTAS)
         bool prerun = k + 1 < my_polys;
         if(prerun) {
           mbar_wait(bars + 16u * (uint32_t)((k + 1) % C::NBAR), (uint32_t)(((k + 1) / C::NBAR) & 1));
-          const size_t nchunk = MULTI ? chunk_of(k + 1) : chunk + gridDim.x;
+          const size_t nchunk = chunk_of(k + 1);
           pass_c_at(sl_next + warp, warp, (uint32_t)(nchunk & (((size_t)1 << s1) - 1)), nchunk, false);
           c1_done = true;
         }
